@@ -1,0 +1,89 @@
+"""In-tree build of the sm_100a libraries (plain nvcc, no torch dependency).
+
+Outputs (git-ignored, shipped to the GPU box by gpurun):
+  accessor-blas_b200/libaccblas_b200.so        the product: kernels + C ABI
+  accessor-blas_b200/libaccblas_baselines.so   cuBLAS baselines (bench only)
+"""
+from __future__ import annotations
+
+import concurrent.futures
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent
+CSRC = HERE / "csrc"
+BUILD = ROOT / "build" / "accblas"
+LIB = HERE / "libaccblas_b200.so"
+BASELINES_LIB = HERE / "libaccblas_baselines.so"
+
+KERNEL_SOURCES = ["capi.cu", "dot.cu", "gemv.cu", "trsv.cu", "convert_fill.cu"]
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON_FLAGS = [
+    "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
+    f"-I{ROOT / 'include'}", f"-I{CSRC}",
+]
+
+
+def _nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        raise RuntimeError("nvcc not found: the accblas libraries cannot be built")
+    return nvcc
+
+
+def _run(cmd: list[str]) -> None:
+    env = dict(os.environ)
+    # the image exports CXX/CC wrappers that break nvcc's host compiler lookup
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("build step failed: " + " ".join(cmd))
+
+
+def _stale(target: Path, deps: list[Path]) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every CUDA translation unit for sm_100a and link the libraries."""
+    nvcc = _nvcc()
+    BUILD.mkdir(parents=True, exist_ok=True)
+    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + \
+        list((ROOT / "include").glob("*.h"))
+
+    def compile_one(name: str) -> Path:
+        src = CSRC / name
+        obj = BUILD / (src.stem + ".o")
+        if force or _stale(obj, [src] + headers):
+            cmd = [nvcc, *COMMON_FLAGS, *ARCH_FLAGS, "-c", str(src), "-o", str(obj)]
+            if verbose:
+                print(" ".join(cmd))
+            _run(cmd)
+        return obj
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as pool:
+        objs = list(pool.map(compile_one, KERNEL_SOURCES + ["baselines.cu"]))
+    kernel_objs = objs[:-1]
+    baseline_obj = objs[-1]
+
+    if force or _stale(LIB, kernel_objs):
+        _run([nvcc, "-shared", *ARCH_FLAGS, "-o", str(LIB),
+              *map(str, kernel_objs), "-cudart", "static"])
+    if force or _stale(BASELINES_LIB, [baseline_obj]):
+        _run([nvcc, "-shared", "-o", str(BASELINES_LIB), str(baseline_obj),
+              "-cudart", "static", "-lcublas",
+              "-Xlinker", "-rpath=/usr/local/cuda/lib64"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,273 @@
+// Shared device/host helpers for the sm_100a accessor-BLAS kernels.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <type_traits>
+
+#include "accblas.h"
+
+namespace accblas {
+
+constexpr int kWarp = 32;
+
+// ---------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------
+struct Handle {
+    int device = 0;
+    int sm_count = 0;
+    // device workspace: [0, 256) bytes control words, then payload
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    // staging buffers of the *_host entry points
+    void* stage[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t stage_bytes[4] = {0, 0, 0, 0};
+    // bytes of the TRSV progress region currently known to hold the sentinel
+    size_t trsv_armed_bytes = 0;
+};
+
+// thread-local error message (accblas_last_error)
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t err, const char* what);
+
+#define ACCBLAS_CUDA(call)                                  \
+    do {                                                    \
+        cudaError_t err__ = (call);                         \
+        if (err__ != cudaSuccess) {                         \
+            return ::accblas::cuda_fail(err__, #call);      \
+        }                                                   \
+    } while (0)
+
+// Makes sure the handle workspace holds at least `bytes` (payload, after the
+// 256-byte control block).  Control block is zeroed on (re)allocation.
+int ensure_workspace(Handle* h, size_t bytes, cudaStream_t stream);
+
+constexpr size_t kControlBytes = 256;
+// control words (unsigned, inside the control block)
+constexpr int kCtlDotCounter = 0;    // DOT "blocks done" counter (self-resetting)
+constexpr int kCtlTrsvTicket = 1;    // TRSV block-row ticket (self-resetting)
+constexpr int kCtlFillFlag = 2;      // fill_uniform non-normal counter
+constexpr int kCtlErrCounter = 3;    // l1_error "blocks done" counter
+
+inline unsigned* control_words(Handle* h)
+{
+    return reinterpret_cast<unsigned*>(h->ws);
+}
+// payload = [scratch for reduction partials | TRSV progress vector]
+constexpr size_t kScratchBytes = size_t{64} << 10;
+inline void* payload(Handle* h)
+{
+    return static_cast<char*>(h->ws) + kControlBytes;
+}
+inline void* trsv_region(Handle* h)
+{
+    return static_cast<char*>(h->ws) + kControlBytes + kScratchBytes;
+}
+
+// ---------------------------------------------------------------------------
+// dtype dispatch
+// ---------------------------------------------------------------------------
+template <accblas_dtype T>
+struct dtype_to_type;
+template <>
+struct dtype_to_type<ACCBLAS_F64> {
+    using type = double;
+};
+template <>
+struct dtype_to_type<ACCBLAS_F32> {
+    using type = float;
+};
+template <>
+struct dtype_to_type<ACCBLAS_F16> {
+    using type = __half;
+};
+
+inline bool valid_dtype(int t) { return t >= 0 && t <= 2; }
+
+// Calls f(St{}, Ar{}) for the (arithmetic, storage) pair; arithmetic must be
+// fp64 or fp32.
+template <typename F>
+int dispatch_ar_st(int ar, int st, F&& f)
+{
+    if (!valid_dtype(ar) || !valid_dtype(st)) {
+        set_error("invalid dtype (ar=%d, st=%d)", ar, st);
+        return ACCBLAS_ERR_INVALID;
+    }
+    if (ar == ACCBLAS_F16) {
+        set_error("fp16 arithmetic is not supported (storage only)");
+        return ACCBLAS_ERR_UNSUPPORTED;
+    }
+    if (ar == ACCBLAS_F64) {
+        switch (st) {
+        case ACCBLAS_F64:
+            return f(double{}, double{});
+        case ACCBLAS_F32:
+            return f(float{}, double{});
+        default:
+            return f(__half{}, double{});
+        }
+    } else {
+        switch (st) {
+        case ACCBLAS_F64:
+            return f(double{}, float{});
+        case ACCBLAS_F32:
+            return f(float{}, float{});
+        default:
+            return f(__half{}, float{});
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------
+#if defined(__CUDACC__)
+
+// storage -> arithmetic (exact widening, or the narrowing static_cast does
+// when St is wider than Ar)
+template <typename Ar, typename St>
+__device__ __forceinline__ Ar to_ar(St v)
+{
+    return static_cast<Ar>(v);
+}
+template <>
+__device__ __forceinline__ float to_ar<float, __half>(__half v)
+{
+    return __half2float(v);
+}
+template <>
+__device__ __forceinline__ double to_ar<double, __half>(__half v)
+{
+    return static_cast<double>(__half2float(v));
+}
+
+// arithmetic -> storage: ONE round-to-nearest-even
+template <typename St, typename Ar>
+__device__ __forceinline__ St to_st(Ar v)
+{
+    return static_cast<St>(v);
+}
+template <>
+__device__ __forceinline__ __half to_st<__half, float>(float v)
+{
+    return __float2half_rn(v);
+}
+template <>
+__device__ __forceinline__ __half to_st<__half, double>(double v)
+{
+    return __double2half(v);
+}
+template <>
+__device__ __forceinline__ __half to_st<__half, __half>(__half v)
+{
+    return v;
+}
+
+// fused multiply-add in the arithmetic type (what nvcc contracts
+// `acc += a * b` to in the reference kernels)
+__device__ __forceinline__ double fma_ar(double a, double b, double c)
+{
+    return fma(a, b, c);
+}
+__device__ __forceinline__ float fma_ar(float a, float b, float c)
+{
+    return fmaf(a, b, c);
+}
+
+// 128-bit streaming load: read-only path, do not allocate in L1 (the matrix /
+// vector stream is touched exactly once)
+__device__ __forceinline__ uint4 ldg_stream_128(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+// 128-bit cached load (x vector in GEMV: re-read by every warp of the SM)
+__device__ __forceinline__ uint4 ldg_cached_128(const void* p)
+{
+    return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+// number of St elements in one 128-bit vector
+template <typename St>
+struct vec_traits {
+    static constexpr int elems = 16 / sizeof(St);
+};
+
+// unpack element `i` (compile-time after unrolling) of a raw 128-bit vector
+template <typename Ar>
+__device__ __forceinline__ Ar unpack(const uint4& raw, int i, double)
+{
+    const unsigned lo = (i == 0) ? raw.x : raw.z;
+    const unsigned hi = (i == 0) ? raw.y : raw.w;
+    return to_ar<Ar, double>(__hiloint2double(hi, lo));
+}
+template <typename Ar>
+__device__ __forceinline__ Ar unpack(const uint4& raw, int i, float)
+{
+    const unsigned w = (i == 0) ? raw.x : (i == 1) ? raw.y : (i == 2) ? raw.z : raw.w;
+    return to_ar<Ar, float>(__uint_as_float(w));
+}
+template <typename Ar>
+__device__ __forceinline__ Ar unpack(const uint4& raw, int i, __half)
+{
+    const int word = i >> 1;
+    const unsigned w = (word == 0) ? raw.x : (word == 1) ? raw.y : (word == 2) ? raw.z : raw.w;
+    const unsigned short bits =
+        static_cast<unsigned short>((i & 1) ? (w >> 16) : (w & 0xffffu));
+    return to_ar<Ar, __half>(__ushort_as_half(bits));
+}
+
+// Converts a raw 128-bit vector of St into vec_traits<St>::elems values of Ar.
+template <typename Ar, typename St>
+__device__ __forceinline__ void unpack_all(const uint4& raw, Ar* out)
+{
+#pragma unroll
+    for (int i = 0; i < vec_traits<St>::elems; ++i) {
+        out[i] = unpack<Ar>(raw, i, St{});
+    }
+}
+
+// warp butterfly sum: fixed order, every lane ends with the same value
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int mask = kWarp / 2; mask > 0; mask >>= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, mask);
+    }
+    return v;
+}
+
+// CTA-wide sum (fixed order): warp butterflies, one smem slot per warp, then
+// warp 0 folds the slots with a second butterfly.  Result valid in thread 0.
+// `scratch` must hold 32 values of T.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch)
+{
+    const int lane = threadIdx.x & (kWarp - 1);
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + kWarp - 1) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // scratch may still be in use by a previous call
+    if (lane == 0) {
+        scratch[warp] = v;
+    }
+    __syncthreads();
+    T total = T{};
+    if (warp == 0) {
+        total = (lane < nwarps) ? scratch[lane] : T{};
+        total = warp_sum(total);
+    }
+    return total;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace accblas

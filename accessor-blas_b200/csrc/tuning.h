@@ -1,0 +1,19 @@
+// Launch-shape knobs.  The defaults are what the library ships with; the
+// setters exist so one GPU session can sweep them (tools/tune.py) -- results
+// are bit-reproducible only for a FIXED configuration, as documented for DOT.
+#pragma once
+
+namespace accblas {
+
+struct Tuning {
+    int dot_unroll = 4;        // 128-bit vectors of each operand in flight per thread
+    int dot_ctas_per_sm = 4;   // grid = SMs * this (256 threads per CTA)
+    int gemv_unroll = 2;       // vectors per row in flight per lane
+    int gemv_variant = 0;      // 0 = auto, 1 = warp-per-4-rows, 2 = CTA-per-2-rows, 3 = CTA-per-row
+    int gemv_ctas_per_sm = 0;  // 0 = all row groups as separate CTAs
+    int trsv_variant = 0;      // 0 = default
+};
+
+Tuning& tuning();
+
+}  // namespace accblas
