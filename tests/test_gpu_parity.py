@@ -1,0 +1,354 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI, against the
+CPU oracle on identical seeded inputs.
+
+Bars (north_star): storage<->arithmetic conversion and the input stream are
+BIT-EXACT; GEMV / DOT / TRSV agree with the accuracy oracle within the
+relative error stated per (arithmetic, storage) pair below, and are no worse
+than the reference's own kernels (order-faithful restatement).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+ST = [torch.float64, torch.float32, torch.float16]
+AR = [torch.float64, torch.float32]
+NP = {torch.float64: np.float64, torch.float32: np.float32, torch.float16: np.float16}
+
+# L1-relative error bar of GEMV (sum|ref-res|/sum|ref|, ref = exact result of
+# the STORED operands) per (arithmetic, storage): the floor is the rounding of
+# the result to storage (u_st/2 on average), plus accumulation error in Ar.
+GEMV_TOL = {
+    (torch.float64, torch.float64): 2e-15,
+    (torch.float64, torch.float32): 6e-8,     # reference plots 3.8e-8..4.2e-8
+    (torch.float64, torch.float16): 5e-4,     # 0.67 * 2^-11 predicted floor
+    (torch.float32, torch.float64): 4e-7,     # inputs cast to fp32, fp32 sums
+    (torch.float32, torch.float32): 4e-7,     # reference plots 0.95e-7..1.5e-7
+    (torch.float32, torch.float16): 5e-4,
+}
+# |res-ref|/|ref| bar for DOT with the result kept in the arithmetic type,
+# scaled by sqrt(n) conditioning of a random uniform(-1,1) dot product
+DOT_TOL = {torch.float64: 5e-14, torch.float32: 2e-5}
+
+
+def dev(a: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def host(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+
+def stored(oracle, count, st, seed=42, first=0):
+    return oracle.convert(oracle.uniform(count, seed=seed, first_draw=first), NP[st])
+
+
+# ---------------------------------------------------------------------------
+# conversion + generation: bit-exact
+# ---------------------------------------------------------------------------
+def special_values():
+    h = np.arange(0, 0x7c00, 37, dtype=np.uint16).view(np.float16).astype(np.float64)
+    mid = (h[:-1] + h[1:]) / 2
+    f = np.array([1 + 2.0 ** -11 + 2.0 ** -30, 65504.0, 65519.99, 65520.0, 1e6,
+                  2.0 ** -24, 2.0 ** -25, 0.0, -0.0, np.inf, -np.inf, 1e-310,
+                  1.0000000596046448, 1 + 2.0 ** -24, 1 + 2.0 ** -24 + 2.0 ** -50,
+                  3.4028235677973366e38, 1e39, 1e-46, 1.4e-45])
+    return np.concatenate([h, -h, mid, -mid, np.nextafter(mid, np.inf), f, -f])
+
+
+@pytest.mark.parametrize("src", ST)
+@pytest.mark.parametrize("dst", ST)
+def test_convert_bit_exact(oracle, handle, src, dst):
+    rng = np.random.default_rng(7)
+    x64 = np.concatenate([special_values(), rng.uniform(-1, 1, 100_003),
+                          rng.uniform(-1e-5, 1e-5, 5000)])
+    x = oracle.convert(x64, NP[src])
+    want = oracle.convert(x, NP[dst])
+    out = torch.empty(x.size, dtype=dst, device=DEV)
+    handle.convert(1, x.size, dev(x), x.size, out, x.size)
+    got = host(out)
+    view = {2: np.uint16, 4: np.uint32, 8: np.uint64}[got.itemsize]
+    assert np.array_equal(got.view(view), want.view(view))
+
+
+@pytest.mark.parametrize("dst", ST)
+def test_convert_strided_rows_and_unaligned(oracle, handle, dst):
+    rows, cols, ld_in, ld_out = 37, 101, 131, 117
+    x = oracle.uniform(rows * ld_in + 1, seed=3)
+    src = dev(x)[1:]  # 8-byte but not 32-byte aligned
+    out = torch.zeros(rows * ld_out, dtype=dst, device=DEV)
+    handle.convert(rows, cols, src, ld_in, out, ld_out)
+    got = host(out).reshape(rows, ld_out)
+    want = oracle.convert(x[1:].reshape(rows, ld_in)[:, :cols].copy(), NP[dst])
+    assert np.array_equal(got[:, :cols].view(np.uint8), want.view(np.uint8))
+    assert not got[:, cols:].any()  # padding untouched
+
+
+@pytest.mark.parametrize("dst", ST)
+@pytest.mark.parametrize("first", [0, 12345, 24500 * 24500, 2 ** 34 + 7])
+def test_fill_uniform_bit_exact(oracle, handle, dst, first):
+    rows, cols, ld = 13, 1001, 1024
+    out = torch.zeros(rows * ld, dtype=dst, device=DEV)
+    handle.fill_uniform(rows, cols, out, ld, seed=42, first_draw=first)
+    got = host(out).reshape(rows, ld)
+    want = oracle.convert(oracle.uniform(rows * cols, seed=42, first_draw=first),
+                          NP[dst]).reshape(rows, cols)
+    assert np.array_equal(got[:, :cols].view(np.uint8), want.view(np.uint8))
+    assert not got[:, cols:].any()
+
+
+def test_fill_uniform_matches_libstdcxx_engine(oracle, handle):
+    n = 50_000
+    out = torch.empty(n, dtype=torch.float64, device=DEV)
+    for seed in (42, 1, 0, 2 ** 31 - 1, 123456789):
+        handle.fill_uniform(1, n, out, n, seed=seed)
+        assert np.array_equal(host(out), oracle.uniform(n, seed=seed, closed_form=False))
+
+
+# ---------------------------------------------------------------------------
+# GEMV
+# ---------------------------------------------------------------------------
+def run_gemv(handle, ar, A, m, n, lda, x, alpha, beta, y, incx=1, incy=1):
+    yd = dev(y)
+    handle.gemv(ar, m, n, alpha, dev(A), lda, dev(x), incx, beta, yd, incy)
+    torch.cuda.synchronize()
+    return host(yd)
+
+
+@pytest.mark.parametrize("ar", AR)
+@pytest.mark.parametrize("st", ST)
+@pytest.mark.parametrize("m,n,lda", [(1, 1, 1), (7, 3, 8), (100, 100, 100),
+                                     (515, 1030, 1032), (33, 4100, 4104),
+                                     (1000, 1000, 24500 if False else 1000),
+                                     (300, 2049, 2056), (2500, 517, 520),
+                                     (20000, 64, 64)])
+def test_gemv_parity(oracle, handle, ar, st, m, n, lda):
+    A = stored(oracle, m * lda, st, first=0)
+    x = stored(oracle, n, st, first=m * lda)
+    y = stored(oracle, m, st, first=m * lda + n)
+    got = run_gemv(handle, ar, A, m, n, lda, x, 1.0, 1.0, y)
+    exact = oracle.exact_gemv(A, m, n, lda, x, 1.0, 1.0, y)
+    err = oracle.l1_rel_error(exact, got)
+    tol = GEMV_TOL[(ar, st)] * max(1.0, np.sqrt(n / 16384))
+    assert err <= tol, (err, tol)
+    # no worse than the reference kernel (same inputs, its summation order)
+    ref = oracle.ref_gemv(NP[ar], A, m, n, lda, x, 1.0, 1.0, y)
+    ref_err = oracle.l1_rel_error(exact, ref)
+    assert err <= 1.5 * ref_err + 1e-16, (err, ref_err)
+
+
+@pytest.mark.parametrize("st", ST)
+def test_gemv_alpha_beta_strides_alignment(oracle, handle, st):
+    m, n, lda, incx, incy = 257, 1031, 1040, 3, 2
+    A = stored(oracle, m * lda + 3, st)
+    x = stored(oracle, n * incx, st, first=10 ** 6)
+    y = stored(oracle, m * incy, st, first=2 * 10 ** 6)
+    for off in (0, 1, 3):                       # misaligned matrix base
+        for alpha, beta in ((0.5, -2.0), (1.0, 0.0), (-1.25, 1.0)):
+            Ao = A[off:off + m * lda].copy()
+            yd = dev(y)
+            Ad = dev(A)[off:]
+            handle.gemv(torch.float64, m, n, alpha, Ad, lda, dev(x), incx, beta, yd, incy)
+            got = host(yd)
+            exact = oracle.exact_gemv(Ao, m, n, lda, x, alpha, beta, y, incx, incy)
+            err = oracle.l1_rel_error(exact, got[::incy].copy())
+            assert err <= GEMV_TOL[(torch.float64, st)], (off, alpha, beta, err)
+            # elements between the strided outputs are untouched
+            assert np.array_equal(got[1::incy], y[1::incy])
+
+
+def test_gemv_beta_zero_ignores_output_nans(oracle, handle):
+    m, n = 129, 513
+    A = stored(oracle, m * n, torch.float32)
+    x = stored(oracle, n, torch.float32, first=m * n)
+    y = np.full(m, np.nan, dtype=np.float32)
+    got = run_gemv(handle, torch.float64, A, m, n, n, x, 1.0, 0.0, y)
+    assert np.isfinite(got).all()
+
+
+def test_gemv_empty_and_errors(ab, handle):
+    y = torch.ones(4, dtype=torch.float32, device=DEV)
+    a = torch.ones(16, dtype=torch.float32, device=DEV)
+    handle.gemv(torch.float64, 0, 4, 1.0, a, 4, y, 1, 1.0, y, 1)  # m == 0: no-op
+    handle.gemv(torch.float64, 4, 0, 1.0, a, 4, y, 1, 2.0, y, 1)  # n == 0: y *= beta
+    torch.cuda.synchronize()
+    assert host(y).tolist() == [2.0] * 4
+    with pytest.raises(ab.AccblasError):
+        handle.gemv(torch.float64, 4, 4, 1.0, a, 3, y, 1, 1.0, y, 1)  # lda < n
+    with pytest.raises(ab.AccblasError):
+        handle.gemv(torch.float16, 4, 4, 1.0, a, 4, y, 1, 1.0, y, 1)  # fp16 arithmetic
+
+
+# ---------------------------------------------------------------------------
+# DOT
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("ar", AR)
+@pytest.mark.parametrize("st", ST)
+@pytest.mark.parametrize("n", [0, 1, 5, 1000, 4097, 2 ** 20, 3_000_001])
+def test_dot_parity_and_determinism(oracle, handle, ar, st, n):
+    x = stored(oracle, max(n, 1), st)[:n]
+    y = stored(oracle, max(n, 1), st, first=max(n, 1))[:n]
+    xd, yd = dev(x) if n else torch.empty(0, dtype=st, device=DEV), \
+        dev(y) if n else torch.empty(0, dtype=st, device=DEV)
+    res = torch.full((1,), -999.0, dtype=ar, device=DEV)  # the reference's sentinel
+    handle.dot(ar, n, xd, 1, yd, 1, res)
+    first = res.clone()
+    exact = oracle.exact_dot(x, y) if n else 0.0
+    got = float(first.item())
+    scale = max(np.sqrt(n / 3.0) / 3.0, abs(exact), 1e-30)
+    assert abs(got - exact) <= DOT_TOL[ar] * scale * max(1.0, np.log2(max(n, 2)) / 20), \
+        (got, exact)
+    for _ in range(3):                              # bit-reproducible run to run
+        res.fill_(-999.0)
+        handle.dot(ar, n, xd, 1, yd, 1, res)
+        assert torch.equal(res, first)
+    if n:
+        ref, _ = oracle.ref_dot(NP[ar], x, y, NP[ar], blocks=148 * 32)
+        assert abs(got - exact) <= 2.0 * abs(float(ref) - exact) + DOT_TOL[ar] * scale * 0.05
+
+
+@pytest.mark.parametrize("st", ST)
+def test_dot_result_types_strides_alignment(oracle, handle, st):
+    n, incx, incy = 70_001, 2, 3
+    x = stored(oracle, n * incx + 1, st)
+    y = stored(oracle, n * incy + 1, st, first=10 ** 6)
+    exact = oracle.exact_dot(x[1:], y[1:], n, incx, incy)
+    for res_t in ST:
+        res = torch.zeros(1, dtype=res_t, device=DEV)
+        handle.dot(torch.float64, n, dev(x)[1:], incx, dev(y)[1:], incy, res)
+        want = oracle.convert(np.array([exact]), NP[res_t])[0]
+        got = host(res)[0]
+        # the fp64 accumulation is far more accurate than one ulp of fp32/fp16,
+        # so the rounded result must be the correctly rounded exact value
+        # (or its neighbour when the exact value sits on a rounding boundary)
+        assert got == want or abs(float(got) - exact) <= 1.5e-12 * abs(exact) + \
+            abs(float(np.spacing(want))), (got, want)
+    # unaligned but contiguous
+    res = torch.zeros(1, dtype=torch.float64, device=DEV)
+    handle.dot(torch.float64, n, dev(x)[1:], 1, dev(y)[1:], 1, res)
+    assert abs(res.item() - oracle.exact_dot(x[1:n + 1].copy(), y[1:n + 1].copy())) < 1e-10
+
+
+# ---------------------------------------------------------------------------
+# TRSV
+# ---------------------------------------------------------------------------
+def lu_fixture(n, seed, lda=None):
+    """Row-major matrix whose triangles are well conditioned the way the
+    reference's fixture is (partially pivoted LU of uniform(-1,1) data,
+    cuda/trsv_memory.cuh:131-168): strict lower = L (|l_ij| <= 1), upper incl.
+    diagonal = U."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    M = (torch.rand(n, n, generator=g, dtype=torch.float64) * 2 - 1).to(DEV)
+    LU, _ = torch.linalg.lu_factor(M)
+    lda = lda or n
+    out = torch.zeros(n, lda, dtype=torch.float64, device=DEV)
+    out[:, :n] = LU
+    return host(out).reshape(-1)
+
+
+TRSV_TOL = {
+    (torch.float64, torch.float64): 1e-11,
+    (torch.float64, torch.float32): 2e-6,
+    (torch.float64, torch.float16): 2e-2,
+    (torch.float32, torch.float64): 5e-4,
+    (torch.float32, torch.float32): 5e-4,
+    (torch.float32, torch.float16): 2e-2,
+}
+
+
+@pytest.mark.parametrize("ar", AR)
+@pytest.mark.parametrize("st", ST)
+@pytest.mark.parametrize("n", [1, 31, 33, 128, 129, 300, 1000])
+@pytest.mark.parametrize("upper,unit,transpose", [(False, True, False),
+                                                  (True, True, True),
+                                                  (True, False, False),
+                                                  (False, False, True)])
+def test_trsv_parity(oracle, ab, handle, ar, st, n, upper, unit, transpose):
+    """unit triangles hold L (or L^T), non-unit ones U (or U^T)."""
+    lda = n + (8 if n > 1 else 0)
+    LU = lu_fixture(n, seed=100 + n, lda=lda).reshape(n, lda)
+    if transpose:
+        T = np.zeros_like(LU)
+        T[:, :n] = LU[:, :n].T
+        LU = T
+    A = oracle.convert(LU.reshape(-1), NP[st])
+    b = stored(oracle, n, st, seed=9)
+    xd = dev(b)
+    handle.trsv(ar, ab.UPPER if upper else ab.LOWER, ab.UNIT if unit else ab.NON_UNIT,
+                n, dev(A), lda, xd, 1)
+    torch.cuda.synchronize()
+    got = host(xd)
+    exact = oracle.exact_trsv(A, n, lda, b, upper, unit)
+    ref = oracle.ref_trsv(NP[ar], A, n, lda, b, upper, unit)
+    err = oracle.l1_rel_error(exact, got)
+    ref_err = oracle.l1_rel_error(exact, ref)
+    if not np.isfinite(ref_err):
+        pytest.skip("fixture not representable in this storage type")
+    # conditioning of U grows with n: bar relative to the reference kernel,
+    # absolute bar for the well-conditioned unit case
+    assert err <= 3.0 * ref_err + 1e-15, (err, ref_err)
+    if unit:
+        assert err <= TRSV_TOL[(ar, st)] * max(1.0, n / 300), (err, ref_err)
+
+
+def test_trsv_repeated_calls_and_strided_x(oracle, ab, handle):
+    n, lda, incx = 700, 704, 2
+    LU = lu_fixture(n, seed=5, lda=lda)
+    A = oracle.convert(LU, np.float32)
+    b = stored(oracle, n * incx, torch.float32, seed=11)
+    exact = oracle.exact_trsv(A, n, lda, b, False, True, incb=incx)
+    Ad = dev(A)
+    outs = []
+    for _ in range(3):  # the workspace must re-arm itself between calls
+        xd = dev(b)
+        handle.trsv(torch.float64, ab.LOWER, ab.UNIT, n, Ad, lda, xd, incx)
+        torch.cuda.synchronize()
+        outs.append(host(xd))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], outs[2])
+    assert np.array_equal(outs[0][1::incx], b[1::incx])
+    assert oracle.l1_rel_error(exact, outs[0][::incx].copy()) < 2e-6
+    # a smaller and a larger system afterwards
+    for n2 in (130, 1500):
+        LU2 = lu_fixture(n2, seed=n2)
+        A2 = oracle.convert(LU2, np.float32)
+        b2 = stored(oracle, n2, torch.float32, seed=12)
+        xd = dev(b2)
+        handle.trsv(torch.float64, ab.LOWER, ab.UNIT, n2, dev(A2), n2, xd, 1)
+        torch.cuda.synchronize()
+        ex2 = oracle.exact_trsv(A2, n2, n2, b2, False, True)
+        assert oracle.l1_rel_error(ex2, host(xd)) < 2e-6 * max(1, n2 / 300)
+
+
+# ---------------------------------------------------------------------------
+# host-buffer entry points (the e2e path of bench.py)
+# ---------------------------------------------------------------------------
+def test_host_entry_points(oracle, ab, handle):
+    m, n = 300, 1001
+    A = stored(oracle, m * n, torch.float32)
+    x = stored(oracle, n, torch.float32, first=m * n)
+    y = stored(oracle, m, torch.float32, first=m * n + n)
+    exact = oracle.exact_gemv(A, m, n, n, x, 1.0, 1.0, y)
+    out = y.copy()
+    handle.gemv_host(torch.float64, m, n, 1.0, A, n, x, 1, 1.0, out, 1)
+    assert oracle.l1_rel_error(exact, out) < 6e-8
+    res = np.zeros(1, dtype=np.float64)
+    handle.dot_host(torch.float64, n, x, 1, A[:n].copy(), 1, res)
+    assert abs(res[0] - oracle.exact_dot(x, A[:n].copy())) < 1e-12
+    nt = 400
+    LU = lu_fixture(nt, seed=77)
+    At = oracle.convert(LU, np.float32)
+    b = stored(oracle, nt, torch.float32, seed=5)
+    sol = b.copy()
+    handle.trsv_host(torch.float64, ab.LOWER, ab.UNIT, nt, At, nt, sol, 1)
+    assert oracle.l1_rel_error(oracle.exact_trsv(At, nt, nt, b, False, True), sol) < 3e-6
+
+
+def test_l1_error_metric_on_device(oracle, handle):
+    n = 100_001
+    ref = oracle.uniform(n, seed=1)
+    res = (ref * (1 + 1e-7)).astype(np.float32)
+    got = handle.l1_error(n, dev(ref), 1, dev(res), 1)
+    want = oracle.l1_rel_error(ref, res)
+    assert got == pytest.approx(want, rel=1e-10)

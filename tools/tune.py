@@ -1,0 +1,70 @@
+"""Launch-shape sweep on a B200 (development tool; run under gpurun).
+
+    python tools/tune.py [dot] [gemv] [trsv]
+
+Prints GB/s (min of 10, the reference's timing protocol) for every storage /
+arithmetic pair at the BASELINE sizes over the tunable launch parameters.
+"""
+import itertools
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import accessor_blas_b200 as ab  # noqa: E402
+from bench import dot_bytes, gemv_bytes, min_of_10  # noqa: E402
+
+NAME = {torch.float64: "fp64", torch.float32: "fp32", torch.float16: "fp16"}
+which = set(sys.argv[1:]) or {"dot", "gemv"}
+dev = torch.device("cuda:0")
+h = ab.Handle(0)
+results = {}
+
+if "dot" in which:
+    n = 2 ** 28
+    for st in (torch.float32, torch.float16, torch.float64):
+        x = torch.empty(n, dtype=st, device=dev)
+        y = torch.empty(n, dtype=st, device=dev)
+        h.fill_uniform(1, n, x, n, 42, 0)
+        h.fill_uniform(1, n, y, n, 42, n)
+        for ar in (torch.float64, torch.float32):
+            res = torch.zeros(1, dtype=ar, device=dev)
+            for unroll, cps in itertools.product((2, 4, 8), (2, 4, 8, 16)):
+                ab.tune("dot_unroll", unroll)
+                ab.tune("dot_ctas_per_sm", cps)
+                ms = min_of_10(lambda: h.dot(ar, n, x, 1, y, 1, res), torch)
+                gbs = dot_bytes(n, x.element_size(), res.element_size()) / ms / 1e6
+                key = f"dot Acc<{NAME[ar]},{NAME[st]}> unroll={unroll} ctas/sm={cps}"
+                results[key] = round(gbs, 1)
+                print(key, f"{gbs:8.1f} GB/s", flush=True)
+        del x, y
+    ab.tune("dot_unroll", 4)
+    ab.tune("dot_ctas_per_sm", 4)
+
+if "gemv" in which:
+    m = k = 16384
+    for st in (torch.float32, torch.float16, torch.float64):
+        A = torch.empty(m * k, dtype=st, device=dev)
+        x = torch.empty(k, dtype=st, device=dev)
+        y = torch.zeros(m, dtype=st, device=dev)
+        h.fill_uniform(m, k, A, k, 42, 0)
+        h.fill_uniform(k, 1, x, 1, 42, m * k)
+        for ar in (torch.float64, torch.float32):
+            for unroll, variant in itertools.product((1, 2, 4), (1, 2, 3)):
+                ab.tune("gemv_unroll", unroll)
+                ab.tune("gemv_variant", variant)
+                ms = min_of_10(lambda: h.gemv(ar, m, k, 1.0, A, k, x, 1, 0.0, y, 1), torch)
+                gbs = gemv_bytes(m, k, A.element_size()) / ms / 1e6
+                key = f"gemv Acc<{NAME[ar]},{NAME[st]}> unroll={unroll} variant={variant}"
+                results[key] = round(gbs, 1)
+                print(key, f"{gbs:8.1f} GB/s", flush=True)
+        del A
+    ab.tune("gemv_unroll", 2)
+    ab.tune("gemv_variant", 0)
+
+out = ROOT / "gpurun_out"
+out.mkdir(exist_ok=True)
+(out / "tune.json").write_text(json.dumps(results, indent=1))
