@@ -82,7 +82,45 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         _run([nvcc, "-shared", "-o", str(BASELINES_LIB), str(baseline_obj),
               "-cudart", "static", "-lcublas",
               "-Xlinker", "-rpath=/usr/local/cuda/lib64"])
+    build_programs(force=force, verbose=verbose)
     return LIB
+
+
+BIN = HERE / "bin"
+PROGRAMS = {
+    # name: (source, extra link flags)
+    "gemv_benchmark": (HERE / "drivers" / "gemv_benchmark.cu", []),
+    "dot_benchmark": (HERE / "drivers" / "dot_benchmark.cu", []),
+    "trsv_benchmark": (HERE / "drivers" / "trsv_benchmark.cu", ["-lcusolver"]),
+    "dropin_test": (ROOT / "tests" / "cpp" / "dropin_test.cu", []),
+}
+
+
+def build_programs(force: bool = False, verbose: bool = False) -> None:
+    """The three benchmark drivers (reference CSV format) and the C++ test of
+    the drop-in header layer, all compiled against include/accblas/*.cuh the
+    way the reference's drivers are compiled against its cuda/*.cuh."""
+    nvcc = _nvcc()
+    BIN.mkdir(exist_ok=True)
+    headers = list((ROOT / "include").rglob("*.*")) + \
+        list((HERE / "drivers").glob("*.cuh")) + [LIB]
+
+    def one(item):
+        name, (src, extra) = item
+        exe = BIN / name
+        if force or _stale(exe, [src] + headers):
+            cmd = [nvcc, "-std=c++17", "-O3", "--expt-relaxed-constexpr", "-lineinfo",
+                   *ARCH_FLAGS, f"-I{ROOT / 'include'}", str(src), "-o", str(exe),
+                   f"-L{HERE}", "-laccblas_b200", "-lcublas", *extra,
+                   "-Xlinker", "-rpath=$ORIGIN/..",
+                   "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+            if verbose:
+                print(" ".join(cmd))
+            _run(cmd)
+        return exe
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=4) as pool:
+        list(pool.map(one, PROGRAMS.items()))
 
 
 if __name__ == "__main__":

@@ -20,7 +20,7 @@ int dot_impl(Handle*, int ar, int st, int res, std::int64_t n, const void* x,
              cudaStream_t);
 int trsv_impl(Handle*, int ar, int st, int uplo, int diag, std::int64_t n,
               const void* A, std::int64_t lda, void* x, std::int64_t incx,
-              cudaStream_t);
+              cudaStream_t, long long* trace = nullptr);
 int convert_impl(Handle*, int dst, int src, std::int64_t rows,
                  std::int64_t cols, const void* in, std::int64_t ld_in,
                  void* out, std::int64_t ld_out, cudaStream_t);
@@ -529,6 +529,19 @@ int accblas_trsv_host(accblas_handle_t handle, accblas_dtype ar,
                                  cudaMemcpyDeviceToHost, s));
     ACCBLAS_CUDA(cudaStreamSynchronize(s));
     return ACCBLAS_OK;
+}
+
+// Development aid (not declared in accblas.h): accblas_trsv that also records
+// 16 phase timestamps per block row into `trace` (device pointer,
+// ceil(n/128)*16 long longs).  Used by tools/trsv_trace.py.
+int accblas_dev_trsv_trace(accblas_handle_t handle, int ar, int st, int uplo,
+                           int diag, int64_t n, const void* A, int64_t lda,
+                           void* x, int64_t incx, long long* trace,
+                           accblas_stream_t stream)
+{
+    ACCBLAS_ENTER(handle);
+    return accblas::trsv_impl(h, ar, st, uplo, diag, n, A, lda, x, incx, s,
+                              trace);
 }
 
 // Development knob (not part of the drop-in surface): set a launch-shape

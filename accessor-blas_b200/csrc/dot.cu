@@ -128,10 +128,18 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     __shared__ Ar scratch[kWarp];
 
     const std::int64_t num_tiles = n / TILE;
-    Ar acc[UNROLL];
+    // fp32 arithmetic: one accumulator per (vector, element) slot, so a chain
+    // is only as long as the number of tiles this CTA walks and the error
+    // stays below the reference's (thread chains of ~55 at n = 2^28).  fp64
+    // arithmetic: one per vector is plenty.
+    constexpr int SLOTS = std::is_same<Ar, float>::value ? VEC : 1;
+    Ar acc[UNROLL][SLOTS];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-        acc[u] = Ar{};
+#pragma unroll
+        for (int i = 0; i < SLOTS; ++i) {
+            acc[u][i] = Ar{};
+        }
     }
 
     for (std::int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -150,9 +158,9 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
         for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                acc[u] = pair_fma<Ar, St>::apply(raw_elem<St>(xr[u], i),
-                                                 raw_elem<St>(yr[u], i),
-                                                 acc[u]);
+                acc[u][i % SLOTS] = pair_fma<Ar, St>::apply(
+                    raw_elem<St>(xr[u], i), raw_elem<St>(yr[u], i),
+                    acc[u][i % SLOTS]);
             }
         }
     }
@@ -166,10 +174,23 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     }
 
     // fixed-order fold of the per-thread accumulators
-    Ar local = acc[0];
+    Ar local = Ar{};
 #pragma unroll
-    for (int u = 1; u < UNROLL; ++u) {
-        local += acc[u];
+    for (int u = 0; u < UNROLL; ++u) {
+        // pairwise fold of the element slots, then the vectors in order
+        Ar v[SLOTS];
+#pragma unroll
+        for (int i = 0; i < SLOTS; ++i) {
+            v[i] = acc[u][i];
+        }
+#pragma unroll
+        for (int width = SLOTS / 2; width > 0; width /= 2) {
+#pragma unroll
+            for (int i = 0; i < width; ++i) {
+                v[i] += v[i + width];
+            }
+        }
+        local += v[0];
     }
     local += tail;
     finish_dot<Ar, BLOCK>(local, partials, counter, result, res_dtype, scratch);

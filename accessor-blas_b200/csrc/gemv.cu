@@ -4,18 +4,24 @@
 // 4/8-byte loads, x re-read and re-converted per element, a shared-memory tree
 // per row; /root/reference/cuda/gemv_kernels.cuh:30-113) with a streaming
 // kernel shaped for B200:
-//   * a warp owns ROWS consecutive rows and walks the columns in chunks of
-//     32 lanes x UNROLL 128-bit vectors, so ROWS*UNROLL independent 16-byte
-//     L1-bypassing loads are in flight per lane and every request is a fully
-//     coalesced 512-byte line group;
-//   * the matching x vectors are loaded once per chunk through L1 (they are
-//     shared by all warps of the SM), converted to the arithmetic type once and
-//     reused for the ROWS rows;
+//   * a CTA owns RG row groups of ROWS consecutive rows; COLW warps share a
+//     row group and walk interleaved column chunks of 32 lanes x UNROLL
+//     128-bit vectors, so ROWS*UNROLL independent 16-byte L1-bypassing loads
+//     are in flight per lane and every request is a fully coalesced 512-byte
+//     line group.  Many small CTAs (thousands) keep the SMs evenly loaded to
+//     the very end of the launch -- measured on B200 the "one warp owns 4
+//     whole rows" shape loses 20 % to the tail, the column-split shape does
+//     not (profiles/r01_tune.md);
+//   * the matching x vectors are loaded once per chunk through L1 (shared by
+//     all CTAs of the SM), converted to the arithmetic type once and reused
+//     for the ROWS rows;
 //   * storage -> arithmetic conversion happens in registers, accumulation is
 //     FMA in the arithmetic type, the row reduction is a warp-shuffle butterfly
-//     (no shared-memory tree, no __syncthreads in the hot loop);
-//   * for short matrices COLW warps share a row group (split columns) and
-//     combine through shared memory in a fixed order.
+//     plus one shared-memory hop between the COLW warps (fixed order);
+//   * fp16 storage with fp64 arithmetic would be bound by the 64-bit
+//     conversion pipe (F2F.F64.F32 issues at a quarter of the rate the HBM
+//     stream needs), so that pair widens with integer bit-field moves instead
+//     (see HalfToDoubleScaled below); results are bit-identical.
 // The result is rounded once to the storage type on the way out, exactly like
 // the accessor's proxy assignment (cuda/gemv_kernels.cuh:106-111).
 #include "common.cuh"
@@ -24,16 +30,63 @@
 namespace accblas {
 namespace {
 
-template <typename Ar, typename St, int ROWS, int UNROLL>
+// ---------------------------------------------------------------------------
+// fp16 -> fp64 without the conversion pipe.
+//
+// Put the 15 magnitude bits of a half h at bits [24:10] of the HIGH word of a
+// double (sign at bit 31, low word 0).  Read as a double this is
+//     d = value(h) * 2^-1008
+// for zero, subnormal and normal h alike: a normal h = 1.m * 2^(e-15) becomes
+// 1.m * 2^(e-1023); a subnormal h = 0.m * 2^-14 becomes the fp64 subnormal
+// 0.m * 2^-1022; fp64 hardware handles subnormal operands at full speed.
+// Multiplying by the pre-scaled x' = x * 2^1008 (exact: |x| <= 65504 keeps x'
+// below DBL_MAX) gives d * x' == value(h) * x as real numbers, and FMA rounds
+// only once, so fma(d, x', acc) == fma(double(h), double(x), acc) bit for bit.
+// Inf/NaN halves (exponent 31) do NOT map correctly; they are detected on the
+// otherwise idle fp16 pipe (0 * h is NaN exactly for those) and the warp
+// recomputes its part with ordinary conversions.
+// Two shifts and a mask per element on the integer pipe instead of one F2F on
+// the quarter-rate pipe.
+// ---------------------------------------------------------------------------
+struct HalfToDoubleScaled {
+    static constexpr unsigned kMask = 0x81FFFC00u;
+    // 2^1008 as a double: exponent field 1008 + 1023 = 2031
+    static __device__ __forceinline__ double scale()
+    {
+        return __hiloint2double(2031 << 20, 0);
+    }
+    static __device__ __forceinline__ double low(unsigned w)
+    {
+        const int v = static_cast<int>(w << 16);
+        return __hiloint2double((v >> 6) & kMask, 0);
+    }
+    static __device__ __forceinline__ double high(unsigned w)
+    {
+        return __hiloint2double((static_cast<int>(w) >> 6) & kMask, 0);
+    }
+};
+
+template <typename Ar, typename St>
+struct use_scaled_half : std::false_type {};
+template <>
+struct use_scaled_half<double, __half> : std::true_type {};
+
+template <typename Ar, typename St, int ROWS, int UNROLL, bool FAST>
 struct ChunkOps {
     static constexpr int VEC = vec_traits<St>::elems;
     static constexpr int CHUNK = kWarp * VEC * UNROLL;
+    // independent accumulators per (row, vector): fp32 arithmetic gets two so
+    // its per-lane chains are as short as the reference's (n / 512 terms)
+    static constexpr int SPLIT = std::is_same<Ar, float>::value ? 2 : 1;
+    static constexpr int SLOTS = UNROLL * SPLIT;
 
-    // full chunk: no predicates
+    // full chunk: no predicates.  `chk` collects NaN iff a non-finite half was
+    // consumed by the FAST path.
     static __device__ __forceinline__ void full(const St* const (&row)[ROWS],
                                                 const St* __restrict__ x,
                                                 std::int64_t c0, int lane,
-                                                Ar (&acc)[ROWS])
+                                                Ar (&acc)[ROWS][SLOTS],
+                                                __half2& chk)
     {
         uint4 xr[UNROLL];
         uint4 ar[ROWS][UNROLL];
@@ -53,12 +106,35 @@ struct ChunkOps {
         for (int u = 0; u < UNROLL; ++u) {
             Ar xv[VEC];
             unpack_all<Ar, St>(xr[u], xv);
-#pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
+            if constexpr (FAST) {
+                const double s = HalfToDoubleScaled::scale();
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
-                    acc[r] = fma_ar(unpack<Ar>(ar[r][u], i, St{}), xv[i],
-                                    acc[r]);
+                    xv[i] = xv[i] * s;
+                }
+                const __half2 zero = __float2half2_rn(0.0f);
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const unsigned w[4] = {ar[r][u].x, ar[r][u].y, ar[r][u].z,
+                                           ar[r][u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[r][u] = fma(HalfToDoubleScaled::low(w[j]),
+                                        xv[2 * j], acc[r][u]);
+                        acc[r][u] = fma(HalfToDoubleScaled::high(w[j]),
+                                        xv[2 * j + 1], acc[r][u]);
+                        chk = __hfma2(*reinterpret_cast<const __half2*>(&w[j]),
+                                      zero, chk);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        Ar& a = acc[r][u * SPLIT + (i % SPLIT)];
+                        a = fma_ar(unpack<Ar>(ar[r][u], i, St{}), xv[i], a);
+                    }
                 }
             }
         }
@@ -67,8 +143,9 @@ struct ChunkOps {
     // last, partial chunk: whole vectors while they fit, then scalars
     static __device__ __forceinline__ void partial(
         const St* const (&row)[ROWS], const St* __restrict__ x,
-        std::int64_t c0, std::int64_t n, int lane, Ar (&acc)[ROWS])
+        std::int64_t c0, std::int64_t n, int lane, Ar (&acc)[ROWS][SLOTS])
     {
+#pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const std::int64_t col = c0 + (u * kWarp + lane) * VEC;
             if (col + VEC <= n) {
@@ -79,7 +156,8 @@ struct ChunkOps {
                     const uint4 a = ldg_stream_128(row[r] + col);
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
-                        acc[r] = fma_ar(unpack<Ar>(a, i, St{}), xv[i], acc[r]);
+                        Ar& t = acc[r][u * SPLIT + (i % SPLIT)];
+                        t = fma_ar(unpack<Ar>(a, i, St{}), xv[i], t);
                     }
                 }
             } else {
@@ -87,7 +165,8 @@ struct ChunkOps {
                     const Ar xv = to_ar<Ar, St>(x[c]);
 #pragma unroll
                     for (int r = 0; r < ROWS; ++r) {
-                        acc[r] = fma_ar(to_ar<Ar, St>(row[r][c]), xv, acc[r]);
+                        Ar& t = acc[r][u * SPLIT];
+                        t = fma_ar(to_ar<Ar, St>(row[r][c]), xv, t);
                     }
                 }
             }
@@ -113,12 +192,15 @@ __device__ __forceinline__ void write_row(St* y, std::int64_t idx, Ar alpha,
 // lda * sizeof(St) a multiple of 16, incx == 1.
 // CTA = RG row groups x COLW column-splitting warps.
 template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW>
-__global__ __launch_bounds__(RG* COLW* kWarp) void gemv_stream_kernel(
+__global__ __launch_bounds__(RG* COLW* kWarp, (ROWS * UNROLL <= 8) ? 3 : 1)
+void gemv_stream_kernel(
     std::int64_t m, std::int64_t n, Ar alpha, const St* __restrict__ A,
     std::int64_t lda, const St* __restrict__ x, Ar beta, St* __restrict__ y,
     std::int64_t incy)
 {
-    using Ops = ChunkOps<Ar, St, ROWS, UNROLL>;
+    constexpr bool FAST = use_scaled_half<Ar, St>::value;
+    using Ops = ChunkOps<Ar, St, ROWS, UNROLL, FAST>;
+    using ExactOps = ChunkOps<Ar, St, ROWS, UNROLL, false>;
     constexpr int CHUNK = Ops::CHUNK;
     const int lane = threadIdx.x & (kWarp - 1);
     const int warp = threadIdx.x >> 5;
@@ -129,10 +211,17 @@ __global__ __launch_bounds__(RG* COLW* kWarp) void gemv_stream_kernel(
     const std::int64_t row0 = group * ROWS;
     const bool active = row0 < m;
 
-    Ar acc[ROWS];
+    // one accumulator per (row, unroll slot): short per-lane chains keep the
+    // fp32-arithmetic rounding error at the level of the reference's
+    // 512-partials-per-row tree
+    constexpr int SLOTS = Ops::SLOTS;
+    Ar part_acc[ROWS][SLOTS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-        acc[r] = Ar{};
+#pragma unroll
+        for (int u = 0; u < SLOTS; ++u) {
+            part_acc[r][u] = Ar{};
+        }
     }
 
     if (active) {
@@ -144,18 +233,41 @@ __global__ __launch_bounds__(RG* COLW* kWarp) void gemv_stream_kernel(
             row[r] = A + ri * lda;
         }
         const std::int64_t full_chunks = n / CHUNK;
-        std::int64_t k = cw;
-        for (; k < full_chunks; k += COLW) {
-            Ops::full(row, x, k * CHUNK, lane, acc);
+        __half2 chk = __float2half2_rn(0.0f);
+        for (std::int64_t k = cw; k < full_chunks; k += COLW) {
+            Ops::full(row, x, k * CHUNK, lane, part_acc, chk);
         }
-        if (k == full_chunks && full_chunks * CHUNK < n) {
-            Ops::partial(row, x, full_chunks * CHUNK, n, lane, acc);
+        if (FAST) {
+            // a non-finite half went through the scaled path: redo this
+            // warp's chunks with ordinary conversions (warp-uniform branch)
+            const float2 c = __half22float2(chk);
+            if (__any_sync(0xffffffffu, (c.x != c.x) || (c.y != c.y))) {
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+                    for (int u = 0; u < SLOTS; ++u) {
+                        part_acc[r][u] = Ar{};
+                    }
+                }
+                for (std::int64_t k = cw; k < full_chunks; k += COLW) {
+                    ExactOps::full(row, x, k * CHUNK, lane, part_acc, chk);
+                }
+            }
+        }
+        if (full_chunks % COLW == cw && full_chunks * CHUNK < n) {
+            Ops::partial(row, x, full_chunks * CHUNK, n, lane, part_acc);
         }
     }
 
+    Ar acc[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-        acc[r] = warp_sum(acc[r]);
+        Ar v = part_acc[r][0];
+#pragma unroll
+        for (int u = 1; u < SLOTS; ++u) {
+            v += part_acc[r][u];
+        }
+        acc[r] = warp_sum(v);
     }
 
     if (COLW == 1) {
@@ -233,23 +345,18 @@ int launch_stream(std::int64_t m, std::int64_t n, Ar alpha, const St* A,
     return ACCBLAS_OK;
 }
 
+// variant: 1 = warp owns 4 whole rows (8 groups per CTA)
+//          2 = CTA owns 2 rows, 8 warps split the columns
+//          3 = CTA owns 1 row,  8 warps split the columns
+//          4 = CTA owns 4 rows, 8 warps split the columns
+//          5 = CTA owns 8 rows (2 groups of 4), 4 warps per group
+//          6 = CTA owns 16 rows (4 groups of 4), 2 warps per group
+//          7 = CTA owns 8 rows (1 group of 8), 8 warps split the columns
 template <typename St, typename Ar, int UNROLL>
-int launch_by_shape(Handle* h, std::int64_t m, std::int64_t n, Ar alpha,
-                    const St* A, std::int64_t lda, const St* x, Ar beta, St* y,
-                    std::int64_t incy, cudaStream_t stream)
+int launch_variant(int variant, std::int64_t m, std::int64_t n, Ar alpha,
+                   const St* A, std::int64_t lda, const St* x, Ar beta, St* y,
+                   std::int64_t incy, cudaStream_t stream)
 {
-    int variant = tuning().gemv_variant;
-    if (variant == 0) {
-        // enough 4-row groups to give every SM >= 16 warps -> warp per group
-        const std::int64_t warps_wanted = std::int64_t{h->sm_count} * 16;
-        if ((m + 3) / 4 >= warps_wanted) {
-            variant = 1;
-        } else if ((m + 1) / 2 >= std::int64_t{h->sm_count} * 2) {
-            variant = 2;
-        } else {
-            variant = 3;
-        }
-    }
     switch (variant) {
     case 1:
         return launch_stream<St, Ar, 4, UNROLL, 8, 1>(m, n, alpha, A, lda, x,
@@ -257,8 +364,20 @@ int launch_by_shape(Handle* h, std::int64_t m, std::int64_t n, Ar alpha,
     case 2:
         return launch_stream<St, Ar, 2, UNROLL, 1, 8>(m, n, alpha, A, lda, x,
                                                       beta, y, incy, stream);
-    default:
+    case 3:
         return launch_stream<St, Ar, 1, UNROLL, 1, 8>(m, n, alpha, A, lda, x,
+                                                      beta, y, incy, stream);
+    case 5:
+        return launch_stream<St, Ar, 4, UNROLL, 2, 4>(m, n, alpha, A, lda, x,
+                                                      beta, y, incy, stream);
+    case 6:
+        return launch_stream<St, Ar, 4, UNROLL, 4, 2>(m, n, alpha, A, lda, x,
+                                                      beta, y, incy, stream);
+    case 7:
+        return launch_stream<St, Ar, 8, UNROLL, 1, 8>(m, n, alpha, A, lda, x,
+                                                      beta, y, incy, stream);
+    default:
+        return launch_stream<St, Ar, 4, UNROLL, 1, 8>(m, n, alpha, A, lda, x,
                                                       beta, y, incy, stream);
     }
 }
@@ -283,16 +402,28 @@ int launch_gemv(Handle* h, std::int64_t m, std::int64_t n, double alpha_d,
           reinterpret_cast<std::uintptr_t>(x)) & 15u) == 0 &&
         (static_cast<std::uint64_t>(lda) * sizeof(St)) % 16 == 0;
     if (vec_ok) {
-        if (tuning().gemv_unroll == 4) {
-            return launch_by_shape<St, Ar, 4>(h, m, n, alpha, A, lda, x, beta,
-                                              y, incy, stream);
+        int variant = tuning().gemv_variant;
+        int unroll = tuning().gemv_unroll;
+        if (variant == 0) {
+            // rows are cheap to split: prefer 4-row CTAs while that still
+            // gives every SM several CTAs, then 2-row, then 1-row CTAs
+            const std::int64_t sms = h->sm_count;
+            variant = (m >= 4 * 8 * sms) ? 4 : (m >= 2 * 4 * sms) ? 2 : 3;
         }
-        if (tuning().gemv_unroll == 1) {
-            return launch_by_shape<St, Ar, 1>(h, m, n, alpha, A, lda, x, beta,
-                                              y, incy, stream);
+        if (unroll == 0) {
+            unroll = 2;
         }
-        return launch_by_shape<St, Ar, 2>(h, m, n, alpha, A, lda, x, beta, y,
-                                          incy, stream);
+        switch (unroll) {
+        case 1:
+            return launch_variant<St, Ar, 1>(variant, m, n, alpha, A, lda, x,
+                                             beta, y, incy, stream);
+        case 4:
+            return launch_variant<St, Ar, 4>(variant, m, n, alpha, A, lda, x,
+                                             beta, y, incy, stream);
+        default:
+            return launch_variant<St, Ar, 2>(variant, m, n, alpha, A, lda, x,
+                                             beta, y, incy, stream);
+        }
     }
     constexpr int BLOCK = 256;
     std::int64_t grid = m;

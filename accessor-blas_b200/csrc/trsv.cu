@@ -125,6 +125,13 @@ __device__ __forceinline__ Quad<St> load_quad(const St* p, int valid)
     return q;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ void group_barrier(int id, int threads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -192,7 +199,7 @@ template <typename St, typename Ar, bool UPPER, bool UNIT, bool VECTOR>
 __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     std::int64_t n, const St* __restrict__ A, std::int64_t lda,
     St* __restrict__ x, std::int64_t incx, Ar* xs,
-    unsigned* __restrict__ ticket)
+    unsigned* __restrict__ ticket, long long* __restrict__ trace)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ar* D = reinterpret_cast<Ar*>(smem_raw);  // kB x kLD
@@ -210,6 +217,12 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     }
     __syncthreads();
     const std::int64_t k = k_shared;  // position in the solve order
+    // development aid: per-CTA phase timestamps (SM cycles / global ns)
+#define ACCBLAS_TRACE(slot, value)                  \
+    if (trace != nullptr && tid == 0) {             \
+        trace[k * 16 + (slot)] = (value);           \
+    }
+    ACCBLAS_TRACE(0, clock64());
     const std::int64_t nb = (n + kB - 1) / kB;
     const std::int64_t pb = UPPER ? nb - 1 - k : k;  // physical block row
     const std::int64_t r0 = pb * kB;
@@ -235,7 +248,9 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
         xsol[tid] = Ar{0};
     }
     __syncthreads();
+    ACCBLAS_TRACE(1, clock64());
     invert_diag_subblocks<Ar, UPPER, UNIT>(D, warp, lane);
+    ACCBLAS_TRACE(2, clock64());
 
     // ---- off-diagonal blocks, in solve order
     Ar acc[kRowsPerWarp];
@@ -261,6 +276,9 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
         for (int i = 0; i < kRowsPerWarp; ++i) {
             raw[i] = load_quad<St, VECTOR>(row_ptr[i] + c0, valid);
         }
+        if (jj == k - 1) {
+            ACCBLAS_TRACE(3, clock64());
+        }
         if (warp == 0) {
             Ar v[kEPL];
             bool ok;
@@ -280,8 +298,15 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
             for (int e = 0; e < kEPL; ++e) {
                 xcol[buf * kB + lane * kEPL + e] = v[e];
             }
+            if (jj == k - 1) {
+                ACCBLAS_TRACE(4, clock64());
+                ACCBLAS_TRACE(13, static_cast<long long>(globaltimer_ns()));
+            }
         }
         __syncthreads();
+        if (jj == k - 1) {
+            ACCBLAS_TRACE(5, clock64());
+        }
         Ar xv[kEPL];
 #pragma unroll
         for (int e = 0; e < kEPL; ++e) {
@@ -311,6 +336,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
         }
     }
     __syncthreads();
+    ACCBLAS_TRACE(6, clock64());
 
     // ---- diagonal block: left-looking over the 32-wide sub-blocks
     for (int step = 0; step < kNSB; ++step) {
@@ -358,7 +384,10 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
             }
         }
         __syncthreads();
+        ACCBLAS_TRACE(7 + step, clock64());
     }
+    ACCBLAS_TRACE(12, static_cast<long long>(globaltimer_ns()));
+#undef ACCBLAS_TRACE
 
     // ---- the last CTA re-arms the workspace for the next call
     if (k == nb - 1) {
@@ -375,7 +404,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
 
 template <typename St, typename Ar, bool UPPER, bool UNIT, bool VECTOR>
 int launch_one(std::int64_t n, const St* A, std::int64_t lda, St* x,
-               std::int64_t incx, Ar* xs, unsigned* ticket,
+               std::int64_t incx, Ar* xs, unsigned* ticket, long long* trace,
                cudaStream_t stream)
 {
     auto kernel = trsv_kernel<St, Ar, UPPER, UNIT, VECTOR>;
@@ -389,7 +418,7 @@ int launch_one(std::int64_t n, const St* A, std::int64_t lda, St* x,
     }
     const std::int64_t nb = (n + kB - 1) / kB;
     kernel<<<static_cast<unsigned>(nb), kThreads, smem, stream>>>(
-        n, A, lda, x, incx, xs, ticket);
+        n, A, lda, x, incx, xs, ticket, trace);
     ACCBLAS_CUDA(cudaGetLastError());
     return ACCBLAS_OK;
 }
@@ -397,7 +426,7 @@ int launch_one(std::int64_t n, const St* A, std::int64_t lda, St* x,
 template <typename St, typename Ar>
 int launch_trsv(Handle* h, int uplo, int diag, std::int64_t n, const void* A_v,
                 std::int64_t lda, void* x_v, std::int64_t incx,
-                cudaStream_t stream)
+                long long* trace, cudaStream_t stream)
 {
     if (n == 0) {
         return ACCBLAS_OK;
@@ -432,7 +461,7 @@ int launch_trsv(Handle* h, int uplo, int diag, std::int64_t n, const void* A_v,
 #define ACCBLAS_TRSV_CASE(U, N, V)                                          \
     if (upper == U && unit == N && vec == V) {                              \
         return launch_one<St, Ar, U, N, V>(n, A, lda, x, incx, xs, ticket,  \
-                                           stream);                         \
+                                           trace, stream);                  \
     }
     ACCBLAS_TRSV_CASE(false, false, false)
     ACCBLAS_TRSV_CASE(false, false, true)
@@ -450,12 +479,13 @@ int launch_trsv(Handle* h, int uplo, int diag, std::int64_t n, const void* A_v,
 
 int trsv_impl(Handle* h, int ar, int st, int uplo, int diag, std::int64_t n,
               const void* A, std::int64_t lda, void* x, std::int64_t incx,
-              cudaStream_t stream)
+              cudaStream_t stream, long long* trace)
 {
     return dispatch_ar_st(ar, st, [&](auto st_tag, auto ar_tag) {
         using St = decltype(st_tag);
         using Ar = decltype(ar_tag);
-        return launch_trsv<St, Ar>(h, uplo, diag, n, A, lda, x, incx, stream);
+        return launch_trsv<St, Ar>(h, uplo, diag, n, A, lda, x, incx, trace,
+                                   stream);
     });
 }
 

@@ -1,0 +1,59 @@
+"""Short program for `ncu`: one launch of each hot kernel at the BASELINE
+sizes after a warm-up launch (so -k regex + -s can pick the warm ones)."""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import accessor_blas_b200 as ab  # noqa: E402
+
+which = set(sys.argv[1:]) or {"gemv", "dot", "trsv"}
+dev = torch.device("cuda:0")
+h = ab.Handle(0)
+f64, f32, f16 = torch.float64, torch.float32, torch.float16
+
+if "gemv" in which:
+    m = n = 16384
+    for st in (f32, f16, f64):
+        A = torch.empty(m * n, dtype=st, device=dev)
+        x = torch.empty(n, dtype=st, device=dev)
+        y = torch.zeros(m, dtype=st, device=dev)
+        h.fill_uniform(m, n, A, n, 42, 0)
+        h.fill_uniform(n, 1, x, 1, 42, m * n)
+        for ar in (f64, f32):
+            for _ in range(2):
+                h.gemv(ar, m, n, 1.0, A, n, x, 1, 1.0, y, 1)
+        torch.cuda.synchronize()
+        del A
+
+if "dot" in which:
+    n = 2 ** 28
+    for st in (f32, f16, f64):
+        x = torch.empty(n, dtype=st, device=dev)
+        y = torch.empty(n, dtype=st, device=dev)
+        h.fill_uniform(1, n, x, n, 42, 0)
+        h.fill_uniform(1, n, y, n, 42, n)
+        for ar in (f64, f32):
+            res = torch.zeros(1, dtype=ar, device=dev)
+            for _ in range(2):
+                h.dot(ar, n, x, 1, y, 1, res)
+        torch.cuda.synchronize()
+        del x, y
+
+if "trsv" in which:
+    n = 16384
+    g = torch.empty(n * n, dtype=torch.float64, device=dev)
+    h.fill_uniform(n, n, g, n, 42, 0)
+    LU, _ = torch.linalg.lu_factor(g.view(n, n))
+    del g
+    A = LU.contiguous().view(-1).to(f32)
+    del LU
+    b = torch.empty(n, dtype=f32, device=dev)
+    h.fill_uniform(n, 1, b, 1, 42, n * n)
+    for _ in range(2):
+        x = b.clone()
+        h.trsv(f64, ab.LOWER, ab.UNIT, n, A, n, x, 1)
+    torch.cuda.synchronize()
+print("profile target done")

@@ -32,7 +32,7 @@ if "dot" in which:
         h.fill_uniform(1, n, y, n, 42, n)
         for ar in (torch.float64, torch.float32):
             res = torch.zeros(1, dtype=ar, device=dev)
-            for unroll, cps in itertools.product((2, 4, 8), (2, 4, 8, 16)):
+            for unroll, cps in itertools.product((2, 4), (4, 8, 16)):
                 ab.tune("dot_unroll", unroll)
                 ab.tune("dot_ctas_per_sm", cps)
                 ms = min_of_10(lambda: h.dot(ar, n, x, 1, y, 1, res), torch)
@@ -53,7 +53,7 @@ if "gemv" in which:
         h.fill_uniform(m, k, A, k, 42, 0)
         h.fill_uniform(k, 1, x, 1, 42, m * k)
         for ar in (torch.float64, torch.float32):
-            for unroll, variant in itertools.product((1, 2, 4), (1, 2, 3)):
+            for unroll, variant in itertools.product((1, 2, 4), (3, 4, 5, 6, 7)):
                 ab.tune("gemv_unroll", unroll)
                 ab.tune("gemv_variant", variant)
                 ms = min_of_10(lambda: h.gemv(ar, m, k, 1.0, A, k, x, 1, 0.0, y, 1), torch)
