@@ -562,6 +562,8 @@ int accblas_tune(const char* key, int value)
         t.gemv_variant = value;
     } else if (!strcmp(key, "gemv_ctas_per_sm")) {
         t.gemv_ctas_per_sm = value;
+    } else if (!strcmp(key, "gemv_stages")) {
+        t.gemv_stages = value;
     } else if (!strcmp(key, "trsv_variant")) {
         t.trsv_variant = value;
     } else {

@@ -102,6 +102,14 @@ struct ChunkOps {
                     ldg_stream_128(row[r] + c0 + (u * kWarp + lane) * VEC);
             }
         }
+        compute(ar, xr, acc, chk);
+    }
+
+    // raw 128-bit vectors (from registers or shared memory) -> accumulators
+    static __device__ __forceinline__ void compute(
+        const uint4 (&ar)[ROWS][UNROLL], const uint4 (&xr)[UNROLL],
+        Ar (&acc)[ROWS][SLOTS], __half2& chk)
+    {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             Ar xv[VEC];
@@ -299,6 +307,309 @@ void gemv_stream_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------
+// Bulk-copy pipelined variant.
+//
+// Same work decomposition and arithmetic as gemv_stream_kernel, but the matrix
+// stream does not pass through registers on its way in: every warp owns a ring
+// of STAGES shared-memory buffers and one lane feeds it with 1-D TMA bulk
+// copies (cp.async.bulk, SASS UBLKCP), one per row and stage, completion
+// signalled on an mbarrier with a transaction count.  The consumer lanes wait on
+// the barrier, read their 16 bytes with LDS.128 and re-arm the stage.  Bytes in
+// flight per warp = STAGES * ROWS * 512 * UNROLL, independent of the register
+// budget, so the HBM pipe stays full while a warp is busy converting.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p)
+{
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar),
+                 "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                     bar),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void* src,
+                                              unsigned bytes, unsigned bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+
+__device__ __forceinline__ uint4 lds_128(unsigned addr)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "r"(addr));
+    return r;
+}
+
+// PERSISTENT: the grid is sized to the machine (CTAs per SM x SMs) and every
+// CTA walks row groups blockIdx.x, blockIdx.x + gridDim.x, ...  The producer
+// lane keeps issuing copies ACROSS row-group boundaries, so the HBM stream
+// never drains while a CTA reduces and writes its rows -- measured on B200 the
+// per-CTA ramp of the non-persistent shape costs 8 % (fp32 rows) to 20 %
+// (fp16 rows) of the bandwidth.
+template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW,
+          int STAGES>
+__global__ __launch_bounds__(RG* COLW* kWarp) void gemv_bulk_kernel(
+    std::int64_t m, std::int64_t n, Ar alpha, const St* __restrict__ A,
+    std::int64_t lda, const St* __restrict__ x, Ar beta, St* __restrict__ y,
+    std::int64_t incy)
+{
+    constexpr bool FAST = use_scaled_half<Ar, St>::value;
+    using Ops = ChunkOps<Ar, St, ROWS, UNROLL, FAST>;
+    using ExactOps = ChunkOps<Ar, St, ROWS, UNROLL, false>;
+    constexpr int CHUNK = Ops::CHUNK;
+    constexpr int VEC = Ops::VEC;
+    constexpr int SLOTS = Ops::SLOTS;
+    constexpr int WARPS = RG * COLW;
+    constexpr unsigned ROW_BYTES = kWarp * 16 * UNROLL;
+    constexpr unsigned STAGE_BYTES = ROWS * ROW_BYTES;
+
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) unsigned long long bars[WARPS][STAGES];
+    __shared__ Ar part[2][RG][COLW][ROWS];
+
+    const int lane = threadIdx.x & (kWarp - 1);
+    const int warp = threadIdx.x >> 5;
+    const int rg = warp / COLW;
+    const int cw = warp % COLW;
+
+    const std::int64_t num_groups = (m + ROWS - 1) / ROWS;
+    const std::int64_t cta_items = (num_groups + RG - 1) / RG;  // per launch
+    // items of this CTA: blockIdx.x + j * gridDim.x
+    const std::int64_t my_items =
+        cta_items > blockIdx.x
+            ? (cta_items - blockIdx.x + gridDim.x - 1) / gridDim.x
+            : 0;
+    const std::int64_t full_chunks = n / CHUNK;
+    // chunks cw, cw + COLW, ... of every row group belong to this warp
+    const std::int64_t count =
+        full_chunks > cw ? (full_chunks - cw + COLW - 1) / COLW : 0;
+    const std::int64_t total = my_items * count;  // ring transactions
+    const unsigned my_ring = smem_u32(ring) + warp * STAGES * STAGE_BYTES;
+    const unsigned my_bars = smem_u32(&bars[warp][0]);
+
+    auto group_of = [&](std::int64_t j) {
+        return (blockIdx.x + j * gridDim.x) * RG + rg;
+    };
+    auto row_ptr = [&](std::int64_t group, int r) {
+        std::int64_t ri = group * ROWS + r;
+        ri = ri < m ? ri : m - 1;  // past the end: re-read a valid row
+        return A + ri * lda;
+    };
+
+    // producer state (lane 0): next transaction to issue
+    std::int64_t issue_j = 0, issue_i = 0, issued = 0;
+    auto issue_next = [&](int stage) {
+        const std::int64_t c0 = (cw + issue_i * COLW) * CHUNK;
+        const std::int64_t g = group_of(issue_j);
+        const unsigned bar = my_bars + stage * 8;
+        mbar_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            bulk_copy_g2s(my_ring + stage * STAGE_BYTES + r * ROW_BYTES,
+                          row_ptr(g, r) + c0, ROW_BYTES, bar);
+        }
+        ++issued;
+        if (++issue_i == count) {
+            issue_i = 0;
+            ++issue_j;
+        }
+    };
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(my_bars + s * 8, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            if (issued < total) {
+                issue_next(s);
+            }
+        }
+    }
+    __syncwarp();
+
+    int stage = 0;
+    unsigned parity = 0;
+    for (std::int64_t j = 0; j < my_items; ++j) {
+        const std::int64_t group = group_of(j);
+        const std::int64_t row0 = group * ROWS;
+        const bool active = row0 < m;
+
+        Ar part_acc[ROWS][SLOTS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+            for (int u = 0; u < SLOTS; ++u) {
+                part_acc[r][u] = Ar{};
+            }
+        }
+        __half2 chk = __float2half2_rn(0.0f);
+        for (std::int64_t i = 0; i < count; ++i) {
+            const std::int64_t c0 = (cw + i * COLW) * CHUNK;
+            uint4 xr[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                xr[u] = ldg_cached_128(x + c0 + (u * kWarp + lane) * VEC);
+            }
+            mbar_wait(my_bars + stage * 8, parity);
+            uint4 ar[ROWS][UNROLL];
+            const unsigned base = my_ring + stage * STAGE_BYTES + lane * 16;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    ar[r][u] = lds_128(base + r * ROW_BYTES + u * kWarp * 16);
+                }
+            }
+            Ops::compute(ar, xr, part_acc, chk);
+            // every lane has consumed its data: the stage can be refilled,
+            // possibly with the first chunk of the NEXT row group
+            __syncwarp();
+            if (lane == 0 && issued < total) {
+                issue_next(stage);
+            }
+            if (++stage == STAGES) {
+                stage = 0;
+                parity ^= 1u;
+            }
+        }
+        if (active) {
+            const St* row[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                row[r] = row_ptr(group, r);
+            }
+            if (FAST) {
+                const float2 c = __half22float2(chk);
+                if (__any_sync(0xffffffffu, (c.x != c.x) || (c.y != c.y))) {
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+                        for (int u = 0; u < SLOTS; ++u) {
+                            part_acc[r][u] = Ar{};
+                        }
+                    }
+                    for (std::int64_t k = cw; k < full_chunks; k += COLW) {
+                        ExactOps::full(row, x, k * CHUNK, lane, part_acc, chk);
+                    }
+                }
+            }
+            if (full_chunks % COLW == cw && full_chunks * CHUNK < n) {
+                Ops::partial(row, x, full_chunks * CHUNK, n, lane, part_acc);
+            }
+        }
+
+        Ar acc[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            Ar v = part_acc[r][0];
+#pragma unroll
+            for (int u = 1; u < SLOTS; ++u) {
+                v += part_acc[r][u];
+            }
+            acc[r] = warp_sum(v);
+        }
+        if (COLW == 1) {
+            if (active && lane < ROWS && row0 + lane < m) {
+                Ar mine = acc[0];
+#pragma unroll
+                for (int r = 1; r < ROWS; ++r) {
+                    mine = (lane == r) ? acc[r] : mine;
+                }
+                write_row<Ar, St>(y, (row0 + lane) * incy, alpha, beta, mine);
+            }
+        } else {
+            // double-buffered by item parity: one barrier per row group
+            const int pb = static_cast<int>(j & 1);
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    part[pb][rg][cw][r] = acc[r];
+                }
+            }
+            __syncthreads();
+            if (active && cw == 0 && lane < ROWS && row0 + lane < m) {
+                Ar sum = part[pb][rg][0][lane];
+#pragma unroll
+                for (int c = 1; c < COLW; ++c) {
+                    sum += part[pb][rg][c][lane];
+                }
+                write_row<Ar, St>(y, (row0 + lane) * incy, alpha, beta, sum);
+            }
+        }
+    }
+}
+
+template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW,
+          int STAGES>
+int launch_bulk(Handle* h, std::int64_t m, std::int64_t n, Ar alpha,
+                const St* A, std::int64_t lda, const St* x, Ar beta, St* y,
+                std::int64_t incy, cudaStream_t stream)
+{
+    auto kernel = gemv_bulk_kernel<St, Ar, ROWS, UNROLL, RG, COLW, STAGES>;
+    constexpr size_t smem =
+        size_t{RG} * COLW * STAGES * ROWS * kWarp * 16 * UNROLL;
+    static int ctas_per_sm = 0;  // per instantiation
+    if (ctas_per_sm == 0) {
+        ACCBLAS_CUDA(cudaFuncSetAttribute(
+            kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            static_cast<int>(smem)));
+        int occ = 0;
+        ACCBLAS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, kernel, RG * COLW * kWarp, smem));
+        ctas_per_sm = occ > 0 ? occ : 1;
+    }
+    const std::int64_t groups = (m + ROWS - 1) / ROWS;
+    const std::int64_t items = (groups + RG - 1) / RG;
+    int per_sm = tuning().gemv_ctas_per_sm;
+    if (per_sm <= 0 || per_sm > ctas_per_sm) {
+        per_sm = ctas_per_sm;
+    }
+    std::int64_t grid = std::int64_t{h->sm_count} * per_sm;
+    if (grid > items) {
+        grid = items;
+    }
+    kernel<<<static_cast<unsigned>(grid), RG * COLW * kWarp, smem, stream>>>(
+        m, n, alpha, A, lda, x, beta, y, incy);
+    ACCBLAS_CUDA(cudaGetLastError());
+    return ACCBLAS_OK;
+}
+
 // Any layout: one CTA per row, scalar (still coalesced for incx == 1) loads.
 template <typename St, typename Ar, int BLOCK>
 __global__ __launch_bounds__(BLOCK) void gemv_generic_kernel(
@@ -352,11 +663,52 @@ int launch_stream(std::int64_t m, std::int64_t n, Ar alpha, const St* A,
 //          5 = CTA owns 8 rows (2 groups of 4), 4 warps per group
 //          6 = CTA owns 16 rows (4 groups of 4), 2 warps per group
 //          7 = CTA owns 8 rows (1 group of 8), 8 warps split the columns
+template <typename St, typename Ar, int UNROLL, int RG, int COLW>
+int launch_bulk_stages(Handle* h, int stages, std::int64_t m, std::int64_t n,
+                       Ar alpha,
+                       const St* A, std::int64_t lda, const St* x, Ar beta,
+                       St* y, std::int64_t incy, cudaStream_t stream)
+{
+    switch (stages) {
+    case 2:
+        return launch_bulk<St, Ar, 4, UNROLL, RG, COLW, 2>(
+            h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+    case 4:
+        return launch_bulk<St, Ar, 4, UNROLL, RG, COLW, 4>(
+            h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+    default:
+        return launch_bulk<St, Ar, 4, UNROLL, RG, COLW, 3>(
+            h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+    }
+}
+
 template <typename St, typename Ar, int UNROLL>
-int launch_variant(int variant, std::int64_t m, std::int64_t n, Ar alpha,
+int launch_variant(Handle* h, int variant, std::int64_t m, std::int64_t n,
+                   Ar alpha,
                    const St* A, std::int64_t lda, const St* x, Ar beta, St* y,
                    std::int64_t incy, cudaStream_t stream)
 {
+    const int stages = tuning().gemv_stages;
+    if (stages > 0 && UNROLL <= 2) {
+        // bulk-copy pipeline: 4-row groups, 8 / 4 / 2 warps per group
+        constexpr int U = UNROLL <= 2 ? UNROLL : 2;
+        switch (variant) {
+        case 5:
+            return launch_bulk_stages<St, Ar, U, 2, 4>(h, stages, m, n, alpha, A,
+                                                       lda, x, beta, y, incy,
+                                                       stream);
+        case 6:
+            return launch_bulk_stages<St, Ar, U, 4, 2>(h, stages, m, n, alpha, A,
+                                                       lda, x, beta, y, incy,
+                                                       stream);
+        case 4:
+            return launch_bulk_stages<St, Ar, U, 1, 8>(h, stages, m, n, alpha, A,
+                                                       lda, x, beta, y, incy,
+                                                       stream);
+        default:
+            break;
+        }
+    }
     switch (variant) {
     case 1:
         return launch_stream<St, Ar, 4, UNROLL, 8, 1>(m, n, alpha, A, lda, x,
@@ -415,13 +767,13 @@ int launch_gemv(Handle* h, std::int64_t m, std::int64_t n, double alpha_d,
         }
         switch (unroll) {
         case 1:
-            return launch_variant<St, Ar, 1>(variant, m, n, alpha, A, lda, x,
+            return launch_variant<St, Ar, 1>(h, variant, m, n, alpha, A, lda, x,
                                              beta, y, incy, stream);
         case 4:
-            return launch_variant<St, Ar, 4>(variant, m, n, alpha, A, lda, x,
+            return launch_variant<St, Ar, 4>(h, variant, m, n, alpha, A, lda, x,
                                              beta, y, incy, stream);
         default:
-            return launch_variant<St, Ar, 2>(variant, m, n, alpha, A, lda, x,
+            return launch_variant<St, Ar, 2>(h, variant, m, n, alpha, A, lda, x,
                                              beta, y, incy, stream);
         }
     }

@@ -137,64 +137,52 @@ __device__ __forceinline__ void group_barrier(int id, int threads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-// In-place inverse of the four 32x32 diagonal sub-blocks of D (row-major,
-// leading dimension kLD).  Same elimination sequence per entry as the
-// reference's Gauss-Jordan (cuda/trsv_kernels.cuh:583-620 / 784-821); rows of
-// one elimination step are independent, so 4 warps share a sub-block.
+// Inverse of one 32x32 triangular sub-block T of D (row-major, leading
+// dimension kLD), in place, by ONE warp: lane j computes column j of T^-1 by
+// substitution entirely in registers (every T(i,k) is a shared-memory
+// broadcast), so the 496 steps of the reference's Gauss-Jordan sweep
+// (/root/reference/cuda/trsv_kernels.cuh:583-620 / 784-821), each separated by
+// a warp barrier, become one barrier-free unrolled pass.
 template <typename Ar, bool UPPER, bool UNIT>
-__device__ __forceinline__ void invert_diag_subblocks(Ar* D, int warp, int lane)
+__device__ __forceinline__ void invert_subblock(Ar* T, Ar* inv_diag, int lane)
 {
-    const int g = warp >> 2;  // sub-block
-    const int q = warp & 3;   // warp inside the group
-    Ar* T = D + (g * kSB) * kLD + g * kSB;
-    const int c = lane;
     if (!UNIT) {
-        for (int row = q; row < kSB; row += 4) {
-            const Ar inv = Ar{1} / T[row * kLD + row];
-            const bool in_tri = UPPER ? (c > row) : (c < row);
-            const Ar cur = T[row * kLD + c];
-            __syncwarp();
-            if (c == row) {
-                T[row * kLD + c] = inv;
-            } else if (in_tri) {
-                T[row * kLD + c] = cur * inv;
-            }
-        }
-        group_barrier(1 + g, 4 * kWarp);
+        inv_diag[lane] = Ar{1} / T[lane * kLD + lane];
     }
-    if (!UPPER) {
-        for (int d = 0; d < kSB; ++d) {
-            const Ar diag_el = T[d * kLD + d];
-            const Ar piv = T[d * kLD + c];
-            for (int row = d + 1 + q; row < kSB; row += 4) {
-                const Ar factor = -T[row * kLD + d];
-                const Ar cur = T[row * kLD + c];
-                __syncwarp();
-                if (c < row) {
-                    T[row * kLD + c] =
-                        (c == d) ? factor * diag_el : fma_ar(factor, piv, cur);
-                }
+    __syncwarp();
+    Ar z[kSB];
+#pragma unroll
+    for (int step = 0; step < kSB; ++step) {
+        const int i = UPPER ? kSB - 1 - step : step;
+        Ar s0 = (i == lane) ? Ar{1} : Ar{0};
+        Ar s1 = Ar{0};
+#pragma unroll
+        for (int t = 0; t < step; ++t) {
+            const int k = UPPER ? kSB - 1 - t : t;
+            const Ar a = T[i * kLD + k];
+            if (t & 1) {
+                s1 = fma_ar(-a, z[k], s1);
+            } else {
+                s0 = fma_ar(-a, z[k], s0);
             }
-            group_barrier(1 + g, 4 * kWarp);
         }
-    } else {
-        for (int d = kSB - 1; d >= 0; --d) {
-            const Ar diag_el = T[d * kLD + d];
-            const Ar piv = T[d * kLD + c];
-            for (int row = d - 1 - q; row >= 0; row -= 4) {
-                const Ar factor = -T[row * kLD + d];
-                const Ar cur = T[row * kLD + c];
-                __syncwarp();
-                if (c > row) {
-                    T[row * kLD + c] =
-                        (c == d) ? factor * diag_el : fma_ar(factor, piv, cur);
-                }
-            }
-            group_barrier(1 + g, 4 * kWarp);
-        }
+        const Ar sum = s0 + s1;
+        z[i] = UNIT ? sum : sum * inv_diag[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kSB; ++i) {
+        T[i * kLD + lane] = z[i];
     }
 }
 
+// Thread layout for 128 x 128 tiles: 4 consecutive lanes share a row
+// (row = tid / 4, seg = tid % 4) and a lane owns the columns
+// 16*i + 4*seg + e (i < 8, e < 4).  Each load instruction therefore reads 16
+// consecutive elements per row for 8 rows (full 32-byte sectors), and a row
+// sum needs only TWO shuffle levels -- the shuffle unit handles one warp per
+// cycle per SM, so the previous "lane = column" layout (five levels for each
+// of 8 rows per warp) spent ~1300 cycles of every block step just shuffling.
 template <typename St, typename Ar, bool UPPER, bool UNIT, bool VECTOR>
 __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     std::int64_t n, const St* __restrict__ A, std::int64_t lda,
@@ -206,11 +194,15 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     Ar* xcol = D + kB * kLD;                  // 2 x kB, staged x blocks
     Ar* rhs = xcol + 2 * kB;                  // kB
     Ar* xsol = rhs + kB;                      // kB
+    Ar* inv_diag = xsol + kB;                 // kB
+    Ar* scratch = inv_diag + kB;              // kB, rehearsal right-hand side
     __shared__ unsigned k_shared;
 
     const int tid = threadIdx.x;
     const int lane = tid & (kWarp - 1);
     const int warp = tid >> 5;
+    const int trow = tid >> 2;  // row of the tile this thread works on
+    const int seg = tid & 3;
 
     if (tid == 0) {
         k_shared = atomicAdd(ticket, 1u);
@@ -228,163 +220,241 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     const std::int64_t r0 = pb * kB;
     const int bs = static_cast<int>((n - r0 < kB) ? (n - r0) : kB);
 
-    // ---- diagonal tile -> shared memory (identity padding past the edge)
-    for (int idx = tid; idx < kB * kB; idx += kThreads) {
-        const int r = idx / kB;
-        const int c = idx % kB;
-        const bool in_tri = UPPER ? (c >= r) : (c <= r);
-        Ar val;
-        if (r < bs && c < bs && in_tri) {
-            val = (UNIT && r == c)
-                      ? Ar{1}
-                      : to_ar<Ar, St>(A[(r0 + r) * lda + r0 + c]);
-        } else {
-            val = (r == c) ? Ar{1} : Ar{0};
+    // ---- diagonal tile -> shared memory (identity padding past the edge);
+    //      all eight loads of a thread are issued before the first is used
+    {
+        constexpr int kIters = kB * (kB / kEPL) / kThreads;  // 8
+        Quad<St> q[kIters];
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+            const int idx = tid + it * kThreads;
+            const int r = idx / (kB / kEPL);
+            const int c = (idx % (kB / kEPL)) * kEPL;
+            const int left = bs - c;
+            const int valid =
+                (r < bs) ? (left >= kEPL ? kEPL : (left > 0 ? left : 0)) : 0;
+            const std::int64_t rr = (r < bs) ? r0 + r : r0;
+            q[it] = load_quad<St, VECTOR>(A + rr * lda + r0 + c, valid);
         }
-        D[r * kLD + c] = val;
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+            const int idx = tid + it * kThreads;
+            const int r = idx / (kB / kEPL);
+            const int c = (idx % (kB / kEPL)) * kEPL;
+#pragma unroll
+            for (int e = 0; e < kEPL; ++e) {
+                const int cc = c + e;
+                const bool in_tri = UPPER ? (cc >= r) : (cc <= r);
+                Ar val;
+                if (r < bs && cc < bs && in_tri && !(UNIT && r == cc)) {
+                    val = to_ar<Ar, St>(q[it].v[e]);
+                } else {
+                    val = (r == cc) ? Ar{1} : Ar{0};
+                }
+                D[r * kLD + cc] = val;
+            }
+        }
     }
     if (tid < kB) {
         rhs[tid] = (tid < bs) ? to_ar<Ar, St>(x[(r0 + tid) * incx]) : Ar{0};
+        scratch[tid] = rhs[tid];
         xsol[tid] = Ar{0};
     }
     __syncthreads();
     ACCBLAS_TRACE(1, clock64());
-    invert_diag_subblocks<Ar, UPPER, UNIT>(D, warp, lane);
+    if (warp < kNSB) {
+        invert_subblock<Ar, UPPER, UNIT>(D + (warp * kSB) * kLD + warp * kSB,
+                                         inv_diag + warp * kSB, lane);
+    }
     ACCBLAS_TRACE(2, clock64());
 
-    // ---- off-diagonal blocks, in solve order
-    Ar acc[kRowsPerWarp];
-#pragma unroll
-    for (int i = 0; i < kRowsPerWarp; ++i) {
-        acc[i] = Ar{};
-    }
-    const St* row_ptr[kRowsPerWarp];
-#pragma unroll
-    for (int i = 0; i < kRowsPerWarp; ++i) {
-        std::int64_t r = r0 + warp * kRowsPerWarp + i;
+    // Everything from here to the end of the diagonal solve runs TWICE:
+    // pass 0 is a rehearsal on scratch data with nothing published.  A CTA
+    // executes the reduction + diagonal-solve code exactly once for real, on
+    // the critical path of the whole solve, and at that point none of it is in
+    // the SM's instruction cache (measured: the cold run costs ~2x the warm
+    // one).  The rehearsal happens while the CTA would be waiting for its
+    // predecessors anyway.
+    constexpr int NP = (sizeof(St) == 8) ? 2 : 1;  // panels per 128-col block
+    constexpr int Q = 8 / NP;                      // quads per panel per thread
+    const St* row_ptr;
+    {
+        std::int64_t r = r0 + trow;
         r = (r < n) ? r : n - 1;  // padded rows re-read a valid row
-        row_ptr[i] = A + r * lda;
+        row_ptr = A + r * lda + kEPL * seg;
     }
-    int buf = 0;
-    for (std::int64_t jj = 0; jj < k; ++jj) {
+    auto load_panel = [&](std::int64_t jj, int p, Quad<St> (&dst)[Q]) {
         const std::int64_t pbj = UPPER ? nb - 1 - jj : jj;
-        const std::int64_t c0 = pbj * kB + lane * kEPL;
-        const std::int64_t left = n - c0;
-        const int valid = left >= kEPL ? kEPL : (left > 0 ? static_cast<int>(left) : 0);
-        Quad<St> raw[kRowsPerWarp];
+        const std::int64_t c0 = pbj * kB + p * (16 * Q);
 #pragma unroll
-        for (int i = 0; i < kRowsPerWarp; ++i) {
-            raw[i] = load_quad<St, VECTOR>(row_ptr[i] + c0, valid);
+        for (int i = 0; i < Q; ++i) {
+            const std::int64_t col = c0 + 16 * i + kEPL * seg;
+            const std::int64_t left = n - col;
+            const int valid =
+                left >= kEPL ? kEPL : (left > 0 ? static_cast<int>(left) : 0);
+            dst[i] = load_quad<St, VECTOR>(row_ptr + c0 + 16 * i, valid);
         }
-        if (jj == k - 1) {
-            ACCBLAS_TRACE(3, clock64());
+    };
+
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool real = pass == 1;
+        Ar* rhs_cur = real ? rhs : scratch;
+        Ar acc[4] = {Ar{}, Ar{}, Ar{}, Ar{}};
+        const std::int64_t deps = real ? k : 0;
+
+        // ---- off-diagonal blocks, in solve order; the loads of the next
+        //      panel are in flight while the current one is consumed
+        Quad<St> cur[Q];
+        if (deps > 0) {
+            load_panel(0, 0, cur);
         }
-        if (warp == 0) {
-            Ar v[kEPL];
-            bool ok;
-            do {
-                ok = true;
+        int buf = 0;
+        for (std::int64_t jj = 0; jj < deps; ++jj) {
 #pragma unroll
-                for (int e = 0; e < kEPL; ++e) {
-                    if (e < valid) {
-                        v[e] = ld_volatile(xs + c0 + e);
-                        ok = ok && !Sentinel<Ar>::is(v[e]);
-                    } else {
-                        v[e] = Ar{0};
+            for (int p = 0; p < NP; ++p) {
+                Quad<St> nxt[Q];
+                if (p + 1 < NP) {
+                    load_panel(jj, p + 1, nxt);
+                } else if (jj + 1 < deps) {
+                    load_panel(jj + 1, 0, nxt);
+                }
+                if (p == 0) {
+                    if (jj == deps - 1) {
+                        ACCBLAS_TRACE(3, clock64());
+                    }
+                    if (warp == 0) {
+                        const std::int64_t pbj = UPPER ? nb - 1 - jj : jj;
+                        const std::int64_t pc = pbj * kB + lane * kEPL;
+                        const std::int64_t left = n - pc;
+                        const int valid =
+                            left >= kEPL
+                                ? kEPL
+                                : (left > 0 ? static_cast<int>(left) : 0);
+                        Ar v[kEPL];
+                        bool ok;
+                        do {
+                            ok = true;
+#pragma unroll
+                            for (int e = 0; e < kEPL; ++e) {
+                                if (e < valid) {
+                                    v[e] = ld_volatile(xs + pc + e);
+                                    ok = ok && !Sentinel<Ar>::is(v[e]);
+                                } else {
+                                    v[e] = Ar{0};
+                                }
+                            }
+                        } while (!__all_sync(0xffffffffu, ok));
+#pragma unroll
+                        for (int e = 0; e < kEPL; ++e) {
+                            xcol[buf * kB + lane * kEPL + e] = v[e];
+                        }
+                        if (jj == deps - 1) {
+                            ACCBLAS_TRACE(4, clock64());
+                            ACCBLAS_TRACE(13, static_cast<long long>(
+                                                  globaltimer_ns()));
+                        }
+                    }
+                    __syncthreads();
+                    if (jj == deps - 1) {
+                        ACCBLAS_TRACE(5, clock64());
                     }
                 }
-            } while (!__all_sync(0xffffffffu, ok));
+                const Ar* xb = xcol + buf * kB + p * (16 * Q) + kEPL * seg;
 #pragma unroll
-            for (int e = 0; e < kEPL; ++e) {
-                xcol[buf * kB + lane * kEPL + e] = v[e];
+                for (int i = 0; i < Q; ++i) {
+#pragma unroll
+                    for (int e = 0; e < kEPL; ++e) {
+                        acc[i & 3] = fma_ar(to_ar<Ar, St>(cur[i].v[e]),
+                                            xb[16 * i + e], acc[i & 3]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < Q; ++i) {
+                    cur[i] = nxt[i];
+                }
             }
-            if (jj == k - 1) {
-                ACCBLAS_TRACE(4, clock64());
-                ACCBLAS_TRACE(13, static_cast<long long>(globaltimer_ns()));
+            buf ^= 1;
+        }
+        {
+            Ar v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (seg == 0 && r0 + trow < n) {  // padded rows stay zero
+                rhs_cur[trow] -= v;
             }
         }
         __syncthreads();
-        if (jj == k - 1) {
-            ACCBLAS_TRACE(5, clock64());
+        if (real) {
+            ACCBLAS_TRACE(6, clock64());
         }
-        Ar xv[kEPL];
-#pragma unroll
-        for (int e = 0; e < kEPL; ++e) {
-            xv[e] = xcol[buf * kB + lane * kEPL + e];
-        }
-#pragma unroll
-        for (int i = 0; i < kRowsPerWarp; ++i) {
-#pragma unroll
-            for (int e = 0; e < kEPL; ++e) {
-                acc[i] = fma_ar(to_ar<Ar, St>(raw[i].v[e]), xv[e], acc[i]);
-            }
-        }
-        buf ^= 1;
-    }
-#pragma unroll
-    for (int i = 0; i < kRowsPerWarp; ++i) {
-        acc[i] = warp_sum(acc[i]);
-    }
-    if (lane < kRowsPerWarp) {
-        Ar mine = acc[0];
-#pragma unroll
-        for (int i = 1; i < kRowsPerWarp; ++i) {
-            mine = (lane == i) ? acc[i] : mine;
-        }
-        if (r0 + warp * kRowsPerWarp + lane < n) {  // padded rows stay zero
-            rhs[warp * kRowsPerWarp + lane] -= mine;
-        }
-    }
-    __syncthreads();
-    ACCBLAS_TRACE(6, clock64());
 
-    // ---- diagonal block: left-looking over the 32-wide sub-blocks
-    for (int step = 0; step < kNSB; ++step) {
-        const int s = UPPER ? kNSB - 1 - step : step;
-        if (step > 0) {
-            // rhs_s -= D[s, solved sub-blocks] * xsol[solved]
-            const int first_col = UPPER ? (s + 1) * kSB : 0;
-            const int ncols = step * kSB;
+        // ---- diagonal block: the four 32-wide sub-blocks in solve order.
+        //      The 128 threads whose rows are in the current sub-block
+        //      multiply by its inverse; then every later row subtracts the
+        //      new solution entries.
+#pragma unroll 1
+        for (int step = 0; step < kNSB; ++step) {
+            const int s = UPPER ? kNSB - 1 - step : step;
+            const int c8 = s * kSB + 8 * seg;
+            if ((trow >> 5) == s) {
+                const Ar* Trow = D + trow * kLD + c8;
+                const Ar* v = rhs_cur + c8;
+                Ar p0 = Ar{}, p1 = Ar{};
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int r = s * kSB + warp * 2 + rr;
-                Ar sum = Ar{};
-                for (int cc = lane; cc < ncols; cc += kWarp) {
-                    sum = fma_ar(D[r * kLD + first_col + cc],
-                                 xsol[first_col + cc], sum);
+                for (int e = 0; e < 8; e += 2) {
+                    p0 = fma_ar(Trow[e], v[e], p0);
+                    p1 = fma_ar(Trow[e + 1], v[e + 1], p1);
                 }
-                sum = warp_sum(sum);
-                if (lane == 0) {
-                    rhs[r] -= sum;
+                Ar sol = p0 + p1;
+                sol += __shfl_xor_sync(0xffffffffu, sol, 1);
+                sol += __shfl_xor_sync(0xffffffffu, sol, 2);
+                if (seg == 0) {
+                    // round through storage: later rows see what the
+                    // accessor re-reads
+                    const St stored = to_st<St, Ar>(sol);
+                    const Ar back = to_ar<Ar, St>(stored);
+                    xsol[trow] = back;
+                    const std::int64_t gi = r0 + trow;
+                    if (real && gi < n) {
+                        st_volatile(xs + gi, Sentinel<Ar>::clean(back));
+                        x[gi * incx] = stored;
+                    }
+                    if (real && step == 1 && trace != nullptr &&
+                        (trow & 31) == 0) {
+                        trace[k * 16 + 14] = clock64();
+                    }
                 }
             }
             __syncthreads();
-        }
-        if (warp == 0) {
-            const int r = s * kSB + lane;
-            const Ar* Trow = D + r * kLD + s * kSB;
-            const Ar* v = rhs + s * kSB;
-            Ar p0 = Ar{}, p1 = Ar{}, p2 = Ar{}, p3 = Ar{};
+            if (real && step == 1) {
+                ACCBLAS_TRACE(15, clock64());
+            }
+            if (step + 1 < kNSB) {
+                const bool later =
+                    UPPER ? ((trow >> 5) < s) : ((trow >> 5) > s);
+                if (later) {
+                    const Ar* Drow = D + trow * kLD + c8;
+                    const Ar* xv = xsol + c8;
+                    Ar p0 = Ar{}, p1 = Ar{};
 #pragma unroll
-            for (int cidx = 0; cidx < kSB; cidx += 4) {
-                p0 = fma_ar(Trow[cidx + 0], v[cidx + 0], p0);
-                p1 = fma_ar(Trow[cidx + 1], v[cidx + 1], p1);
-                p2 = fma_ar(Trow[cidx + 2], v[cidx + 2], p2);
-                p3 = fma_ar(Trow[cidx + 3], v[cidx + 3], p3);
+                    for (int e = 0; e < 8; e += 2) {
+                        p0 = fma_ar(Drow[e], xv[e], p0);
+                        p1 = fma_ar(Drow[e + 1], xv[e + 1], p1);
+                    }
+                    Ar sum = p0 + p1;
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    if (seg == 0) {
+                        rhs_cur[trow] -= sum;
+                    }
+                }
+                __syncthreads();
             }
-            const Ar sol = (p0 + p1) + (p2 + p3);
-            // round through storage: later rows see what the accessor re-reads
-            const St stored = to_st<St, Ar>(sol);
-            const Ar back = to_ar<Ar, St>(stored);
-            xsol[r] = back;
-            const std::int64_t gi = r0 + r;
-            if (gi < n) {
-                st_volatile(xs + gi, Sentinel<Ar>::clean(back));
-                x[gi * incx] = stored;
+            if (real) {
+                ACCBLAS_TRACE(7 + step, clock64());
             }
         }
-        __syncthreads();
-        ACCBLAS_TRACE(7 + step, clock64());
     }
     ACCBLAS_TRACE(12, static_cast<long long>(globaltimer_ns()));
 #undef ACCBLAS_TRACE
@@ -408,7 +478,7 @@ int launch_one(std::int64_t n, const St* A, std::int64_t lda, St* x,
                cudaStream_t stream)
 {
     auto kernel = trsv_kernel<St, Ar, UPPER, UNIT, VECTOR>;
-    const size_t smem = sizeof(Ar) * (kB * kLD + 4 * kB);
+    const size_t smem = sizeof(Ar) * (kB * kLD + 6 * kB);
     static bool configured = false;  // per instantiation
     if (!configured) {
         ACCBLAS_CUDA(cudaFuncSetAttribute(

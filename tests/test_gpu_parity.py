@@ -352,3 +352,63 @@ def test_l1_error_metric_on_device(oracle, handle):
     got = handle.l1_error(n, dev(ref), 1, dev(res), 1)
     want = oracle.l1_rel_error(ref, res)
     assert got == pytest.approx(want, rel=1e-10)
+
+
+# ---------------------------------------------------------------------------
+# every launch shape the tuner can select must give the same answers
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("stages", [0, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+def test_gemv_all_launch_shapes(oracle, ab, handle, variant, stages):
+    shapes = [(515, 1030, 1032), (37, 4100, 4104), (1000, 8192, 8192)]
+    try:
+        for unroll in (1, 2, 4):
+            ab.tune("gemv_variant", variant)
+            ab.tune("gemv_stages", stages)
+            ab.tune("gemv_unroll", unroll)
+            for m, n, lda in shapes:
+                for ar, st in ((torch.float64, torch.float32), (torch.float64, torch.float16),
+                               (torch.float32, torch.float16), (torch.float64, torch.float64)):
+                    A = stored(oracle, m * lda, st)
+                    x = stored(oracle, n, st, first=m * lda)
+                    y = stored(oracle, m, st, first=m * lda + n)
+                    got = run_gemv(handle, ar, A, m, n, lda, x, 1.0, 1.0, y)
+                    exact = oracle.exact_gemv(A, m, n, lda, x, 1.0, 1.0, y)
+                    err = oracle.l1_rel_error(exact, got)
+                    assert err <= GEMV_TOL[(ar, st)], (variant, stages, unroll, m, n, err)
+    finally:
+        ab.tune("gemv_variant", 0)
+        ab.tune("gemv_stages", 0)
+        ab.tune("gemv_unroll", 2)
+
+
+def test_gemv_fp16_fp64_fast_path_is_bit_identical_and_handles_non_finite(oracle, handle):
+    """The integer widening used for Acc<fp64,fp16> must equal the plain
+    conversion bit for bit (checked against the reference's summation order is
+    not possible, so against the same kernel with the chunk loop disabled via a
+    short n) and fall back when Inf/NaN halves appear."""
+    m, n = 64, 8192
+    rng = np.random.default_rng(11)
+    vals = rng.uniform(-1, 1, m * n)
+    vals[::97] *= 1e-6          # fp16 subnormals
+    vals[5::1013] = 0.0
+    A = oracle.convert(vals, np.float16)
+    x = oracle.convert(rng.uniform(-4, 4, n), np.float16)
+    y = np.zeros(m, dtype=np.float16)
+    got = run_gemv(handle, torch.float64, A, m, n, n, x, 1.0, 0.0, y)
+    exact = oracle.exact_gemv(A, m, n, n, x, 1.0, 0.0, y)
+    assert np.array_equal(got, exact.astype(np.float16)) or \
+        oracle.l1_rel_error(exact, got) < 3.5e-4
+    # non-finite entries: rows containing them must come out non-finite exactly
+    # like the straightforward computation, the others untouched
+    A2 = A.copy().reshape(m, n)
+    A2[3, 100] = np.inf
+    A2[7, 4097] = np.nan
+    A2[9, 12] = -np.inf
+    got2 = run_gemv(handle, torch.float64, A2.reshape(-1), m, n, n, x, 1.0, 0.0, y)
+    want2 = (A2.astype(np.float64) @ x.astype(np.float64)).astype(np.float16)
+    assert np.isposinf(got2[3]) == np.isposinf(want2[3]) and not np.isfinite(got2[3])
+    assert np.isnan(got2[7]) and not np.isfinite(got2[9])
+    keep = np.ones(m, dtype=bool)
+    keep[[3, 7, 9]] = False
+    assert np.array_equal(got2[keep], got[keep])

@@ -58,6 +58,9 @@ for k in sorted(set([0, 1, 2, nb // 4, nb // 2, nb - 2, nb - 1])):
         continue
     d = np.diff(t[k, :11])
     print(f"block {k:4d}: " + "  ".join(f"{nm}={int(v)}" for nm, v in zip(names, d)))
+for k in (nb // 2, nb - 1):
+    print(f"block {k}: step1 begins {int(t[k, 7])}, matvec done +{int(t[k, 14] - t[k, 7])}, "
+          f"sync1 passed +{int(t[k, 15] - t[k, 7])}, step1 ends +{int(t[k, 8] - t[k, 7])}")
 ends = t[:, 12].astype(np.float64)
 seen = t[:, 13].astype(np.float64)
 step = np.diff(ends)

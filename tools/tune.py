@@ -53,17 +53,19 @@ if "gemv" in which:
         h.fill_uniform(m, k, A, k, 42, 0)
         h.fill_uniform(k, 1, x, 1, 42, m * k)
         for ar in (torch.float64, torch.float32):
-            for unroll, variant in itertools.product((1, 2, 4), (3, 4, 5, 6, 7)):
+            for unroll, variant, stages in itertools.product((1, 2), (4, 5, 6), (0, 2, 3, 4)):
                 ab.tune("gemv_unroll", unroll)
                 ab.tune("gemv_variant", variant)
+                ab.tune("gemv_stages", stages)
                 ms = min_of_10(lambda: h.gemv(ar, m, k, 1.0, A, k, x, 1, 0.0, y, 1), torch)
                 gbs = gemv_bytes(m, k, A.element_size()) / ms / 1e6
-                key = f"gemv Acc<{NAME[ar]},{NAME[st]}> unroll={unroll} variant={variant}"
+                key = f"gemv Acc<{NAME[ar]},{NAME[st]}> unroll={unroll} variant={variant} stages={stages}"
                 results[key] = round(gbs, 1)
                 print(key, f"{gbs:8.1f} GB/s", flush=True)
         del A
     ab.tune("gemv_unroll", 2)
     ab.tune("gemv_variant", 0)
+    ab.tune("gemv_stages", 0)
 
 out = ROOT / "gpurun_out"
 out.mkdir(exist_ok=True)
