@@ -31,6 +31,8 @@ int l1_error_impl(Handle*, int ref_t, int res_t, std::int64_t n,
                   const void* ref, std::int64_t inc_ref, const void* res,
                   std::int64_t inc_res, double* out2, cudaStream_t);
 
+int set_gemv_trace(unsigned long long* ptr);
+
 namespace {
 thread_local char g_error[512] = "";
 Tuning g_tuning;
@@ -544,6 +546,13 @@ int accblas_dev_trsv_trace(accblas_handle_t handle, int ar, int st, int uplo,
                               trace);
 }
 
+// Development aid: per-CTA start/end timestamps of the next GEMV launches
+// (3 x grid unsigned long longs, device pointer; nullptr switches it off).
+int accblas_dev_gemv_trace(unsigned long long* trace)
+{
+    return accblas::set_gemv_trace(trace);
+}
+
 // Development knob (not part of the drop-in surface): set a launch-shape
 // parameter by name.  Returns ACCBLAS_ERR_INVALID for unknown keys.
 int accblas_tune(const char* key, int value)
@@ -564,6 +573,8 @@ int accblas_tune(const char* key, int value)
         t.gemv_ctas_per_sm = value;
     } else if (!strcmp(key, "gemv_stages")) {
         t.gemv_stages = value;
+    } else if (!strcmp(key, "gemv_taper")) {
+        t.gemv_taper = value;
     } else if (!strcmp(key, "trsv_variant")) {
         t.trsv_variant = value;
     } else {

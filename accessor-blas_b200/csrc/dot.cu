@@ -227,6 +227,19 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
 {
     constexpr int VEC = vec_traits<St>::elems;
     constexpr std::int64_t TILE = std::int64_t{BLOCK} * VEC * UNROLL;
+    auto kernel = dot_stream_kernel<St, Ar, BLOCK, UNROLL>;
+    // one resident wave: every CTA of the grid-stride loop is on the machine
+    // from start to end (a partial second wave would leave a tail)
+    static int resident = 0;  // per instantiation
+    if (resident == 0) {
+        int occ = 0;
+        ACCBLAS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, kernel, BLOCK, 0));
+        resident = occ > 0 ? occ : 1;
+    }
+    if (ctas_per_sm <= 0 || ctas_per_sm > resident) {
+        ctas_per_sm = resident;
+    }
     std::int64_t tiles = n / TILE;
     std::int64_t grid = std::int64_t{h->sm_count} * ctas_per_sm;
     if (tiles < grid) {
@@ -240,11 +253,10 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
     if (rc != ACCBLAS_OK) {
         return rc;
     }
-    dot_stream_kernel<St, Ar, BLOCK, UNROLL>
-        <<<static_cast<unsigned>(grid), BLOCK, 0, stream>>>(
-            static_cast<const St*>(x), static_cast<const St*>(y), n,
-            static_cast<Ar*>(payload(h)), control_words(h) + kCtlDotCounter,
-            result, res);
+    kernel<<<static_cast<unsigned>(grid), BLOCK, 0, stream>>>(
+        static_cast<const St*>(x), static_cast<const St*>(y), n,
+        static_cast<Ar*>(payload(h)), control_words(h) + kCtlDotCounter,
+        result, res);
     ACCBLAS_CUDA(cudaGetLastError());
     return ACCBLAS_OK;
 }

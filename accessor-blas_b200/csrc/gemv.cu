@@ -28,7 +28,25 @@
 #include "tuning.h"
 
 namespace accblas {
+
+// development aid: when non-null, every CTA of gemv_stream_kernel records its
+// start / end time (globaltimer ns) and SM id at [3*blockIdx.x ...]
+__device__ unsigned long long* g_gemv_trace = nullptr;
+
+int set_gemv_trace(unsigned long long* ptr)
+{
+    ACCBLAS_CUDA(cudaMemcpyToSymbol(g_gemv_trace, &ptr, sizeof(ptr)));
+    return ACCBLAS_OK;
+}
+
 namespace {
+
+__device__ __forceinline__ unsigned long long gemv_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ---------------------------------------------------------------------------
 // fp16 -> fp64 without the conversion pipe.
@@ -196,36 +214,28 @@ __device__ __forceinline__ void write_row(St* y, std::int64_t idx, Ar alpha,
     y[idx] = to_st<St, Ar>(out);
 }
 
-// Requirements (checked by the launcher): A and x 16-byte aligned,
-// lda * sizeof(St) a multiple of 16, incx == 1.
-// CTA = RG row groups x COLW column-splitting warps.
-template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW>
-__global__ __launch_bounds__(RG* COLW* kWarp, (ROWS * UNROLL <= 8) ? 3 : 1)
-void gemv_stream_kernel(
+// One row group of R rows: the COLW warps that share it walk the column chunks,
+// reduce and write.  `part` is the CTA's [RG][COLW][MAXR] staging array.
+template <typename St, typename Ar, int R, int MAXR, int UNROLL, int COLW>
+__device__ __forceinline__ void gemv_row_group(
     std::int64_t m, std::int64_t n, Ar alpha, const St* __restrict__ A,
     std::int64_t lda, const St* __restrict__ x, Ar beta, St* __restrict__ y,
-    std::int64_t incy)
+    std::int64_t incy, std::int64_t row0, int rg, int cw, int lane,
+    Ar (*part)[COLW][MAXR])
 {
     constexpr bool FAST = use_scaled_half<Ar, St>::value;
-    using Ops = ChunkOps<Ar, St, ROWS, UNROLL, FAST>;
-    using ExactOps = ChunkOps<Ar, St, ROWS, UNROLL, false>;
+    using Ops = ChunkOps<Ar, St, R, UNROLL, FAST>;
+    using ExactOps = ChunkOps<Ar, St, R, UNROLL, false>;
     constexpr int CHUNK = Ops::CHUNK;
-    const int lane = threadIdx.x & (kWarp - 1);
-    const int warp = threadIdx.x >> 5;
-    const int rg = warp / COLW;  // row group inside the CTA
-    const int cw = warp % COLW;  // column slot inside the row group
-
-    const std::int64_t group = std::int64_t{blockIdx.x} * RG + rg;
-    const std::int64_t row0 = group * ROWS;
+    constexpr int SLOTS = Ops::SLOTS;
     const bool active = row0 < m;
 
     // one accumulator per (row, unroll slot): short per-lane chains keep the
     // fp32-arithmetic rounding error at the level of the reference's
     // 512-partials-per-row tree
-    constexpr int SLOTS = Ops::SLOTS;
-    Ar part_acc[ROWS][SLOTS];
+    Ar part_acc[R][SLOTS];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
+    for (int r = 0; r < R; ++r) {
 #pragma unroll
         for (int u = 0; u < SLOTS; ++u) {
             part_acc[r][u] = Ar{};
@@ -233,9 +243,9 @@ void gemv_stream_kernel(
     }
 
     if (active) {
-        const St* row[ROWS];
+        const St* row[R];
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
+        for (int r = 0; r < R; ++r) {
             // rows past the end re-read the last valid row; never written
             const std::int64_t ri = (row0 + r < m) ? row0 + r : m - 1;
             row[r] = A + ri * lda;
@@ -251,7 +261,7 @@ void gemv_stream_kernel(
             const float2 c = __half22float2(chk);
             if (__any_sync(0xffffffffu, (c.x != c.x) || (c.y != c.y))) {
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
+                for (int r = 0; r < R; ++r) {
 #pragma unroll
                     for (int u = 0; u < SLOTS; ++u) {
                         part_acc[r][u] = Ar{};
@@ -267,9 +277,9 @@ void gemv_stream_kernel(
         }
     }
 
-    Ar acc[ROWS];
+    Ar acc[R];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
+    for (int r = 0; r < R; ++r) {
         Ar v = part_acc[r][0];
 #pragma unroll
         for (int u = 1; u < SLOTS; ++u) {
@@ -279,24 +289,23 @@ void gemv_stream_kernel(
     }
 
     if (COLW == 1) {
-        if (active && lane < ROWS && row0 + lane < m) {
+        if (active && lane < R && row0 + lane < m) {
             Ar mine = acc[0];
 #pragma unroll
-            for (int r = 1; r < ROWS; ++r) {
+            for (int r = 1; r < R; ++r) {
                 mine = (lane == r) ? acc[r] : mine;
             }
             write_row<Ar, St>(y, (row0 + lane) * incy, alpha, beta, mine);
         }
     } else {
-        __shared__ Ar part[RG][COLW][ROWS];
         if (lane == 0) {
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
+            for (int r = 0; r < R; ++r) {
                 part[rg][cw][r] = acc[r];
             }
         }
         __syncthreads();
-        if (active && cw == 0 && lane < ROWS && row0 + lane < m) {
+        if (active && cw == 0 && lane < R && row0 + lane < m) {
             Ar sum = part[rg][0][lane];
 #pragma unroll
             for (int c = 1; c < COLW; ++c) {
@@ -304,6 +313,59 @@ void gemv_stream_kernel(
             }
             write_row<Ar, St>(y, (row0 + lane) * incy, alpha, beta, sum);
         }
+    }
+}
+
+// Requirements (checked by the launcher): A and x 16-byte aligned,
+// lda * sizeof(St) a multiple of 16, incx == 1.
+// CTA = RG row groups x COLW column-splitting warps.
+//
+// Row groups are handed out in blockIdx order, which is also the order the
+// hardware dispatches CTAs in.  CTAs below b_full own ROWS rows per group, the
+// next b_half own ROWS/2 and the rest ROWS/4: the CTAs that start last are
+// short, so the machine drains in a fraction of the time (measured tail of the
+// uniform shape at 16384^2 fp32: 11 us of a 164 us kernel).  The size class is
+// uniform per CTA, so each class runs its own unpredicated instantiation.
+template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW>
+__global__ __launch_bounds__(RG* COLW* kWarp, (ROWS * UNROLL <= 8) ? 3 : 1)
+void gemv_stream_kernel(
+    std::int64_t m, std::int64_t n, Ar alpha, const St* __restrict__ A,
+    std::int64_t lda, const St* __restrict__ x, Ar beta, St* __restrict__ y,
+    std::int64_t incy, std::int64_t b_full, std::int64_t b_half)
+{
+    constexpr int HALF = ROWS >= 2 ? ROWS / 2 : 1;
+    constexpr int QUARTER = ROWS >= 4 ? ROWS / 4 : 1;
+    __shared__ Ar part[RG][COLW][ROWS];
+    const int lane = threadIdx.x & (kWarp - 1);
+    const int warp = threadIdx.x >> 5;
+    const int rg = warp / COLW;  // row group inside the CTA
+    const int cw = warp % COLW;  // column slot inside the row group
+    unsigned long long* const trace = g_gemv_trace;
+    if (trace != nullptr && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        trace[3 * blockIdx.x] = gemv_globaltimer();
+        trace[3 * blockIdx.x + 2] = smid;
+    }
+
+    const std::int64_t b = blockIdx.x;
+    if (b < b_full) {
+        const std::int64_t row0 = (b * RG + rg) * ROWS;
+        gemv_row_group<St, Ar, ROWS, ROWS, UNROLL, COLW>(
+            m, n, alpha, A, lda, x, beta, y, incy, row0, rg, cw, lane, part);
+    } else if (b < b_full + b_half) {
+        const std::int64_t row0 =
+            b_full * RG * ROWS + ((b - b_full) * RG + rg) * HALF;
+        gemv_row_group<St, Ar, HALF, ROWS, UNROLL, COLW>(
+            m, n, alpha, A, lda, x, beta, y, incy, row0, rg, cw, lane, part);
+    } else {
+        const std::int64_t row0 = b_full * RG * ROWS + b_half * RG * HALF +
+                                  ((b - b_full - b_half) * RG + rg) * QUARTER;
+        gemv_row_group<St, Ar, QUARTER, ROWS, UNROLL, COLW>(
+            m, n, alpha, A, lda, x, beta, y, incy, row0, rg, cw, lane, part);
+    }
+    if (trace != nullptr && threadIdx.x == 0) {
+        trace[3 * blockIdx.x + 1] = gemv_globaltimer();
     }
 }
 
@@ -639,19 +701,39 @@ __global__ __launch_bounds__(BLOCK) void gemv_generic_kernel(
 }
 
 template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW>
-int launch_stream(std::int64_t m, std::int64_t n, Ar alpha, const St* A,
-                  std::int64_t lda, const St* x, Ar beta, St* y,
+int launch_stream(Handle* h, std::int64_t m, std::int64_t n, Ar alpha,
+                  const St* A, std::int64_t lda, const St* x, Ar beta, St* y,
                   std::int64_t incy, cudaStream_t stream)
 {
-    const std::int64_t groups = (m + ROWS - 1) / ROWS;
-    const std::int64_t grid = (groups + RG - 1) / RG;
+    auto kernel = gemv_stream_kernel<St, Ar, ROWS, UNROLL, RG, COLW>;
+    static int resident = 0;  // CTAs per SM, per instantiation
+    if (resident == 0) {
+        int occ = 0;
+        ACCBLAS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, kernel, RG * COLW * kWarp, 0));
+        resident = occ > 0 ? occ : 1;
+    }
+    // taper: the last two "waves" of CTAs own half / a quarter of the rows
+    constexpr int HALF = ROWS >= 2 ? ROWS / 2 : 1;
+    constexpr int QUARTER = ROWS >= 4 ? ROWS / 4 : 1;
+    const std::int64_t slots = std::int64_t{h->sm_count} * resident;  // CTAs
+    std::int64_t b_full, b_half, b_quarter;
+    if (ROWS >= 4 && tuning().gemv_taper != 0 && m >= 4 * slots * RG * ROWS) {
+        b_half = slots;
+        b_full = (m - slots * RG * (HALF + QUARTER)) / (RG * ROWS);
+        const std::int64_t rest = m - b_full * RG * ROWS - b_half * RG * HALF;
+        b_quarter = (rest + RG * QUARTER - 1) / (RG * QUARTER);
+    } else {
+        b_full = (m + RG * ROWS - 1) / (RG * ROWS);
+        b_half = b_quarter = 0;
+    }
+    const std::int64_t grid = b_full + b_half + b_quarter;
     if (grid > 0x7fffffffLL) {
         set_error("gemv: too many rows (%lld)", static_cast<long long>(m));
         return ACCBLAS_ERR_INVALID;
     }
-    gemv_stream_kernel<St, Ar, ROWS, UNROLL, RG, COLW>
-        <<<static_cast<unsigned>(grid), RG * COLW * kWarp, 0, stream>>>(
-            m, n, alpha, A, lda, x, beta, y, incy);
+    kernel<<<static_cast<unsigned>(grid), RG * COLW * kWarp, 0, stream>>>(
+        m, n, alpha, A, lda, x, beta, y, incy, b_full, b_half);
     ACCBLAS_CUDA(cudaGetLastError());
     return ACCBLAS_OK;
 }
@@ -711,25 +793,25 @@ int launch_variant(Handle* h, int variant, std::int64_t m, std::int64_t n,
     }
     switch (variant) {
     case 1:
-        return launch_stream<St, Ar, 4, UNROLL, 8, 1>(m, n, alpha, A, lda, x,
+        return launch_stream<St, Ar, 4, UNROLL, 8, 1>(h, m, n, alpha, A, lda, x,
                                                       beta, y, incy, stream);
     case 2:
-        return launch_stream<St, Ar, 2, UNROLL, 1, 8>(m, n, alpha, A, lda, x,
+        return launch_stream<St, Ar, 2, UNROLL, 1, 8>(h, m, n, alpha, A, lda, x,
                                                       beta, y, incy, stream);
     case 3:
-        return launch_stream<St, Ar, 1, UNROLL, 1, 8>(m, n, alpha, A, lda, x,
+        return launch_stream<St, Ar, 1, UNROLL, 1, 8>(h, m, n, alpha, A, lda, x,
                                                       beta, y, incy, stream);
     case 5:
-        return launch_stream<St, Ar, 4, UNROLL, 2, 4>(m, n, alpha, A, lda, x,
+        return launch_stream<St, Ar, 4, UNROLL, 2, 4>(h, m, n, alpha, A, lda, x,
                                                       beta, y, incy, stream);
     case 6:
-        return launch_stream<St, Ar, 4, UNROLL, 4, 2>(m, n, alpha, A, lda, x,
+        return launch_stream<St, Ar, 4, UNROLL, 4, 2>(h, m, n, alpha, A, lda, x,
                                                       beta, y, incy, stream);
     case 7:
-        return launch_stream<St, Ar, 8, UNROLL, 1, 8>(m, n, alpha, A, lda, x,
+        return launch_stream<St, Ar, 8, UNROLL, 1, 8>(h, m, n, alpha, A, lda, x,
                                                       beta, y, incy, stream);
     default:
-        return launch_stream<St, Ar, 4, UNROLL, 1, 8>(m, n, alpha, A, lda, x,
+        return launch_stream<St, Ar, 4, UNROLL, 1, 8>(h, m, n, alpha, A, lda, x,
                                                       beta, y, incy, stream);
     }
 }

@@ -32,7 +32,10 @@ namespace {
 constexpr int kB = 128;       // rows/cols per block row
 constexpr int kSB = 32;       // diagonal sub-block
 constexpr int kNSB = kB / kSB;
-constexpr int kLD = kB + 1;   // padded leading dimension of the smem tile
+// Leading dimension of the smem tile: 136 = 8 * 17, so that 16-byte (two
+// double) loads by 2 rows x 4 column slots per quarter-warp hit eight distinct
+// 16-byte bank groups (row stride 136 doubles = 68 groups = 4 mod 8).
+constexpr int kLD = kB + 8;
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / kWarp;
 constexpr int kRowsPerWarp = kB / kWarps;  // 8
@@ -72,6 +75,22 @@ template <typename T>
 __device__ __forceinline__ void st_volatile(T* p, T v)
 {
     *reinterpret_cast<volatile T*>(p) = v;
+}
+
+template <typename Ar>
+struct alignas(2 * sizeof(Ar)) Pair {
+    Ar a, b;
+};
+
+// keeps a converted value in a register at this point of the program (the
+// compiler would otherwise sink the conversion below the barrier that follows)
+__device__ __forceinline__ void pin_register(double& v)
+{
+    asm volatile("" : "+d"(v));
+}
+__device__ __forceinline__ void pin_register(float& v)
+{
+    asm volatile("" : "+f"(v));
 }
 
 template <typename St>
@@ -212,7 +231,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     // development aid: per-CTA phase timestamps (SM cycles / global ns)
 #define ACCBLAS_TRACE(slot, value)                  \
     if (trace != nullptr && tid == 0) {             \
-        trace[k * 16 + (slot)] = (value);           \
+        trace[k * 64 + (slot)] = (value);           \
     }
     ACCBLAS_TRACE(0, clock64());
     const std::int64_t nb = (n + kB - 1) / kB;
@@ -300,7 +319,14 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     for (int pass = 0; pass < 2; ++pass) {
         const bool real = pass == 1;
         Ar* rhs_cur = real ? rhs : scratch;
-        Ar acc[4] = {Ar{}, Ar{}, Ar{}, Ar{}};
+        // fp32 arithmetic: one accumulator per quad slot, so a chain is no
+        // longer than the reference's (one term per 32-column block)
+        constexpr int NACC = std::is_same<Ar, float>::value ? 8 : 4;
+        Ar acc[NACC];
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) {
+            acc[i] = Ar{};
+        }
         const std::int64_t deps = real ? k : 0;
 
         // ---- off-diagonal blocks, in solve order; the loads of the next
@@ -318,6 +344,19 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                     load_panel(jj, p + 1, nxt);
                 } else if (jj + 1 < deps) {
                     load_panel(jj + 1, 0, nxt);
+                }
+                // widen the panel BEFORE waiting for x: the 64-bit conversions
+                // go through the XU pipe at 16 lanes/clk/SM (1024 cycles for a
+                // 128x128 tile) and would otherwise sit on the critical path
+                // between "x arrived" and "row sums ready"
+                Ar cv[Q][kEPL];
+#pragma unroll
+                for (int i = 0; i < Q; ++i) {
+#pragma unroll
+                    for (int e = 0; e < kEPL; ++e) {
+                        cv[i][e] = to_ar<Ar, St>(cur[i].v[e]);
+                        pin_register(cv[i][e]);
+                    }
                 }
                 if (p == 0) {
                     if (jj == deps - 1) {
@@ -365,8 +404,8 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                 for (int i = 0; i < Q; ++i) {
 #pragma unroll
                     for (int e = 0; e < kEPL; ++e) {
-                        acc[i & 3] = fma_ar(to_ar<Ar, St>(cur[i].v[e]),
-                                            xb[16 * i + e], acc[i & 3]);
+                        const int slot = (p * Q + i) % NACC;
+                        acc[slot] = fma_ar(cv[i][e], xb[16 * i + e], acc[slot]);
                     }
                 }
 #pragma unroll
@@ -377,7 +416,14 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
             buf ^= 1;
         }
         {
-            Ar v = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+            for (int width = NACC / 2; width > 0; width /= 2) {
+#pragma unroll
+                for (int i = 0; i < width; ++i) {
+                    acc[i] += acc[i + width];
+                }
+            }
+            Ar v = acc[0];
             v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
             if (seg == 0 && r0 + trow < n) {  // padded rows stay zero
@@ -396,51 +442,57 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
 #pragma unroll 1
         for (int step = 0; step < kNSB; ++step) {
             const int s = UPPER ? kNSB - 1 - step : step;
-            const int c8 = s * kSB + 8 * seg;
+            // a thread owns the column pairs 32 s + 2 seg + 8 e + {0, 1}
+            const int c2 = s * kSB + 2 * seg;
+            const bool probe = real && trace != nullptr && seg == 0;
             if ((trow >> 5) == s) {
-                const Ar* Trow = D + trow * kLD + c8;
-                const Ar* v = rhs_cur + c8;
+                if (probe && (trow & 31) == 0) {
+                    trace[k * 64 + 16 + 4 * step] = clock64();
+                }
+                const Pair<Ar>* Trow =
+                    reinterpret_cast<const Pair<Ar>*>(D + trow * kLD + c2);
+                const Pair<Ar>* v =
+                    reinterpret_cast<const Pair<Ar>*>(rhs_cur + c2);
                 Ar p0 = Ar{}, p1 = Ar{};
 #pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                    p0 = fma_ar(Trow[e], v[e], p0);
-                    p1 = fma_ar(Trow[e + 1], v[e + 1], p1);
+                for (int e = 0; e < 4; ++e) {
+                    const Pair<Ar> t = Trow[4 * e];
+                    const Pair<Ar> w = v[4 * e];
+                    p0 = fma_ar(t.a, w.a, p0);
+                    p1 = fma_ar(t.b, w.b, p1);
                 }
                 Ar sol = p0 + p1;
                 sol += __shfl_xor_sync(0xffffffffu, sol, 1);
                 sol += __shfl_xor_sync(0xffffffffu, sol, 2);
                 if (seg == 0) {
                     // round through storage: later rows see what the
-                    // accessor re-reads
+                    // accessor re-reads.  NOT published here: a global store
+                    // in front of a CTA barrier makes the barrier wait for
+                    // the store's round trip to L2 (~700 cycles per sub-step
+                    // measured); the whole block is published after the loop.
                     const St stored = to_st<St, Ar>(sol);
-                    const Ar back = to_ar<Ar, St>(stored);
-                    xsol[trow] = back;
-                    const std::int64_t gi = r0 + trow;
-                    if (real && gi < n) {
-                        st_volatile(xs + gi, Sentinel<Ar>::clean(back));
-                        x[gi * incx] = stored;
-                    }
-                    if (real && step == 1 && trace != nullptr &&
-                        (trow & 31) == 0) {
-                        trace[k * 16 + 14] = clock64();
+                    xsol[trow] = to_ar<Ar, St>(stored);
+                    if (probe && (trow & 31) == 0) {
+                        trace[k * 64 + 17 + 4 * step] = clock64();
                     }
                 }
             }
             __syncthreads();
-            if (real && step == 1) {
-                ACCBLAS_TRACE(15, clock64());
-            }
             if (step + 1 < kNSB) {
                 const bool later =
                     UPPER ? ((trow >> 5) < s) : ((trow >> 5) > s);
                 if (later) {
-                    const Ar* Drow = D + trow * kLD + c8;
-                    const Ar* xv = xsol + c8;
+                    const Pair<Ar>* Drow =
+                        reinterpret_cast<const Pair<Ar>*>(D + trow * kLD + c2);
+                    const Pair<Ar>* xv =
+                        reinterpret_cast<const Pair<Ar>*>(xsol + c2);
                     Ar p0 = Ar{}, p1 = Ar{};
 #pragma unroll
-                    for (int e = 0; e < 8; e += 2) {
-                        p0 = fma_ar(Drow[e], xv[e], p0);
-                        p1 = fma_ar(Drow[e + 1], xv[e + 1], p1);
+                    for (int e = 0; e < 4; ++e) {
+                        const Pair<Ar> t = Drow[4 * e];
+                        const Pair<Ar> w = xv[4 * e];
+                        p0 = fma_ar(t.a, w.a, p0);
+                        p1 = fma_ar(t.b, w.b, p1);
                     }
                     Ar sum = p0 + p1;
                     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
@@ -448,11 +500,25 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                     if (seg == 0) {
                         rhs_cur[trow] -= sum;
                     }
+                    const int next_s = UPPER ? s - 1 : s + 1;
+                    if (probe && trow == 32 * next_s) {
+                        trace[k * 64 + 18 + 4 * step] = clock64();
+                    }
                 }
                 __syncthreads();
             }
             if (real) {
                 ACCBLAS_TRACE(7 + step, clock64());
+            }
+        }
+        if (real && seg == 0) {
+            // publish the solved block: progress vector first (that is what
+            // the next block row is spinning on), then the caller's x
+            const std::int64_t gi = r0 + trow;
+            if (gi < n) {
+                const Ar val = xsol[trow];
+                st_volatile(xs + gi, Sentinel<Ar>::clean(val));
+                x[gi * incx] = to_st<St, Ar>(val);
             }
         }
     }

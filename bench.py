@@ -407,6 +407,9 @@ def run_accblas_arm(args):
     h = ab.Handle(local_rank)
     peak, peak_kind = measured_peak()
 
+    if args.workload == "config5":
+        return run_config5(args, ab, sharded, h, torch, dist, world, rank, dev, barrier, peak)
+
     # -- workload: this rank's slab of the row-sharded (M*world) x N matrix ------
     m_total, n = M * world, N_COLS
     first, rows = sharded.row_partition(m_total, world, rank)
@@ -555,12 +558,83 @@ def run_accblas_arm(args):
         dist.destroy_process_group()
 
 
+def run_config5(args, ab, sharded, h, torch, dist, world, rank, dev, barrier, peak):
+    """BASELINE.json configs[4]: FIXED total problem, sharded over the ranks
+    (strong scaling): GEMV m = n = 131072 fp32 storage (64 GiB) row-sharded with
+    x broadcast once, and DOT n = 2^32 fp32 range-sharded with one 1-element
+    NCCL all-reduce per call.  Acc<fp64, fp32>."""
+    st, ar, s = torch.float32, torch.float64, 4
+    m_total = n = 131072
+    first, rows = sharded.row_partition(m_total, world, rank)
+    A = torch.empty(rows * n, dtype=st, device=dev)
+    x = torch.empty(n, dtype=st, device=dev)
+    y = torch.empty(rows, dtype=st, device=dev)
+    h.fill_uniform(rows, n, A, n, 42, first * n)
+    if rank == 0:
+        h.fill_uniform(n, 1, x, 1, 42, m_total * n)
+    sharded.broadcast_vector(x)
+    h.fill_uniform(rows, 1, y, 1, 42, m_total * n + n + first)
+    gemv = sharded.ShardedGemv(h, ar, m_total, n, n)
+    steps, warmup = min(args.steps, 20), min(args.warmup, 5)
+    ms = time_launches(lambda: gemv(1.0, A, x, 1.0, y), steps, warmup, torch, barrier)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    gemv_total = gemv_bytes(m_total, n, s)
+    checksum = float(y.double().abs().sum().item())
+    del A
+    torch.cuda.empty_cache()
+
+    nd = 2 ** 32
+    d_first, d_count = sharded.range_partition(nd, world, rank)
+    xd = torch.empty(d_count, dtype=st, device=dev)
+    yd = torch.empty(d_count, dtype=st, device=dev)
+    h.fill_uniform(1, d_count, xd, d_count, 42, d_first)
+    h.fill_uniform(1, d_count, yd, d_count, 42, nd + d_first)
+    sdot = sharded.ShardedDot(h, ar, nd)
+    dot_ms = time_launches(lambda: sdot(xd, yd, torch.float32), steps, warmup, torch, barrier)
+    if world > 1:
+        t = torch.tensor([dot_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dot_ms = float(t.item())
+    dot_value = float(sdot(xd, yd, torch.float64).item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": gemv_total / (ms * 1e-3) / 1e9, "unit": "GB/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[4]: row-sharded GEMV m=n=131072 fp32 storage "
+                                   "(64 GiB) + DOT n=2^32 with one NCCL all-reduce, "
+                                   "Acc<fp64,fp32>", "rows_per_gpu": rows,
+                       "l2": "inputs exceed L2"},
+            "roofline": {"bound": "hbm", "achieved": gemv_bytes(rows, n, s) / (ms * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s",
+                         "frac": gemv_bytes(rows, n, s) / (ms * 1e-3) / 1e9 / peak,
+                         "traffic": None},
+            "gpu_launches": steps * world,
+            "extra": {"gemv_abs_checksum_rank0_slab": checksum,
+                      "dot": {"n": nd, "ms_per_step": dot_ms,
+                              "GBps": dot_bytes(nd, s, 4) / (dot_ms * 1e-3) / 1e9,
+                              "result": dot_value,
+                              "collective": "1-element all_reduce(SUM) per call"
+                              if world > 1 else "none (N=1)"}},
+        }), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="accblas", choices=["accblas", "reference"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
+                    help="config2 = BASELINE configs[1] (default, weak scaling); "
+                         "config5 = BASELINE configs[4] (fixed 64 GiB GEMV + 2^32 DOT, strong)")
     ap.add_argument("--no-detail", action="store_true",
                     help="skip the per-pair / cuBLAS / TRSV detail table")
     args = ap.parse_args()

@@ -38,7 +38,7 @@ b = torch.empty(n, dtype=torch.float64, device=dev)
 h.fill_uniform(n, 1, b, 1, 42, n * n)
 b = b.to(st)
 nb = (n + 127) // 128
-trace = torch.zeros(nb * 16, dtype=torch.int64, device=dev)
+trace = torch.zeros(nb * 64, dtype=torch.int64, device=dev)
 for it in range(3):
     x = b.clone()
     trace.zero_()
@@ -50,7 +50,7 @@ for it in range(3):
     torch.cuda.synchronize()
     assert rc == 0
     print(f"run {it}: {e0.elapsed_time(e1) * 1e3:.1f} us total")
-t = trace.cpu().numpy().reshape(nb, 16)
+t = trace.cpu().numpy().reshape(nb, 64)
 names = ["load diag", "invert", "(wait) ->issue last", "poll last x", "release", "tile+reduce",
          "sub0", "sub1", "sub2", "sub3"]
 for k in sorted(set([0, 1, 2, nb // 4, nb // 2, nb - 2, nb - 1])):
@@ -59,8 +59,14 @@ for k in sorted(set([0, 1, 2, nb // 4, nb // 2, nb - 2, nb - 1])):
     d = np.diff(t[k, :11])
     print(f"block {k:4d}: " + "  ".join(f"{nm}={int(v)}" for nm, v in zip(names, d)))
 for k in (nb // 2, nb - 1):
-    print(f"block {k}: step1 begins {int(t[k, 7])}, matvec done +{int(t[k, 14] - t[k, 7])}, "
-          f"sync1 passed +{int(t[k, 15] - t[k, 7])}, step1 ends +{int(t[k, 8] - t[k, 7])}")
+    base = t[k, 6]
+    parts = []
+    for step in range(4):
+        b, r, u = (int(t[k, 16 + 4 * step + i] - base) for i in range(3))
+        parts.append(f"step{step}: matvec begin +{b}, sol ready +{r}" +
+                     (f", update done +{u}" if step < 3 else ""))
+    print(f"block {k} (cycles after the row-sum barrier): " + "; ".join(parts) +
+          f"; loop end +{int(t[k, 10] - base)}")
 ends = t[:, 12].astype(np.float64)
 seen = t[:, 13].astype(np.float64)
 step = np.diff(ends)
