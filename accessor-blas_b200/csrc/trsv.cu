@@ -400,6 +400,13 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                     }
                 }
                 const Ar* xb = xcol + buf * kB + p * (16 * Q) + kEPL * seg;
+                const bool tile_probe =
+                    trace != nullptr && tid == 0 && jj == deps - 1 && p == NP - 1;
+                if (tile_probe) {
+                    Ar first = xb[0];
+                    pin_register(first);
+                    trace[k * 64 + 32] = clock64();
+                }
 #pragma unroll
                 for (int i = 0; i < Q; ++i) {
 #pragma unroll
@@ -407,6 +414,13 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                         const int slot = (p * Q + i) % NACC;
                         acc[slot] = fma_ar(cv[i][e], xb[16 * i + e], acc[slot]);
                     }
+                }
+                if (tile_probe) {
+#pragma unroll
+                    for (int i = 0; i < NACC; ++i) {
+                        pin_register(acc[i]);
+                    }
+                    trace[k * 64 + 33] = clock64();
                 }
 #pragma unroll
                 for (int i = 0; i < Q; ++i) {
@@ -428,6 +442,10 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
             v += __shfl_xor_sync(0xffffffffu, v, 2);
             if (seg == 0 && r0 + trow < n) {  // padded rows stay zero
                 rhs_cur[trow] -= v;
+            }
+            if (real && trace != nullptr && tid == 0) {
+                pin_register(v);
+                trace[k * 64 + 34] = clock64();
             }
         }
         __syncthreads();

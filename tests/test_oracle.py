@@ -193,3 +193,65 @@ def test_cpu_baseline_matches_exact(oracle):
         assert oracle.l1_rel_error(exact, got) < tol
         d = oracle.cpu_dot(np.float64, x, A[:n].copy(), np.float64)
         assert abs(d - oracle.exact_dot(x, A[:n].copy())) < 1e-11
+
+
+# --- golden outputs of the reference's own CUDA kernels (generated on a B200) ---
+def _reference_golden():
+    path = GOLDEN / "reference_kernels_b200.npz"
+    if not path.exists():
+        pytest.skip("tests/golden/reference_kernels_b200.npz not generated yet")
+    return np.load(path)
+
+
+_DT = {"f64": np.float64, "f32": np.float32}
+
+
+def test_oracle_matches_reference_cuda_kernels_gemv_bitwise():
+    """The order-faithful GEMV restatement equals what the reference's kernels
+    produced on the B200, bit for bit (tests/golden/make_reference_golden.py)."""
+    from oracle_binding import Oracle
+    orc = Oracle()
+    g = _reference_golden()
+    keys = [k for k in g.files if k.startswith("gemv_")]
+    assert keys
+    for key in keys:
+        _, m, n, lda, ar, st, plain = key.split("_")
+        m, n, lda = int(m), int(n), int(lda)
+        A = orc.convert(orc.uniform(m * lda, seed=42), _DT[st])
+        x = orc.convert(orc.uniform(n, seed=42, first_draw=m * lda), _DT[st])
+        y = orc.convert(orc.uniform(m, seed=42, first_draw=m * lda + n), _DT[st])
+        want = orc.ref_gemv(_DT[ar], A, m, n, lda, x, 1.0, 1.0, y)
+        assert np.array_equal(want.view(np.uint8), g[key].view(np.uint8)), key
+
+
+def test_oracle_matches_reference_cuda_kernels_dot_and_trsv():
+    from oracle_binding import Oracle
+    orc = Oracle()
+    g = _reference_golden()
+    blocks = int(g["sm_count"][0]) * 32
+    for key in [k for k in g.files if k.startswith("dot_")]:
+        _, n, ar, st, res, plain = key.split("_")
+        n = int(n)
+        x = orc.convert(orc.uniform(n, seed=42), _DT[st])
+        y = orc.convert(orc.uniform(n, seed=42, first_draw=n), _DT[st])
+        want, partials = orc.ref_dot(_DT[ar], x, y, _DT[res], blocks=blocks)
+        # the GPU combines the block partials with atomics in arbitrary order
+        eps = 2.3e-16 if ar == "f64" else 1.2e-7
+        slack = 4 * eps * np.abs(partials.astype(np.float64)).sum() + \
+            (6e-8 * abs(float(want)) if res == "f32" else 0.0)
+        assert abs(float(g[key][0]) - float(want)) <= slack, key
+    for key in [k for k in g.files if k.startswith("trsv_")]:
+        _, n, upper, unit, ar, st, plain = key.split("_")
+        n, upper, unit = int(n), int(upper), int(unit)
+        base = orc.uniform(n * n, seed=7).reshape(n, n) * 0.02
+        T = base.copy()
+        np.fill_diagonal(T, 1.0 + 0.5 * orc.uniform(n, seed=8))
+        A = orc.convert(T.reshape(-1), _DT[st])
+        b = orc.convert(orc.uniform(n, seed=9), _DT[st])
+        want = orc.ref_trsv(_DT[ar], A, n, n, b, upper, unit)
+        got = g[key]
+        if np.array_equal(want.view(np.uint8), got.view(np.uint8)):
+            continue
+        exact = orc.exact_trsv(A, n, n, b, upper, unit)
+        e_got, e_want = orc.l1_rel_error(exact, got), orc.l1_rel_error(exact, want)
+        assert e_got <= 1.5 * e_want + 1e-15 and e_want <= 1.5 * e_got + 1e-15, key

@@ -9,7 +9,12 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import accessor_blas_b200 as ab  # noqa: E402
 
-which = set(sys.argv[1:]) or {"gemv", "dot", "trsv"}
+# usage: profile_target.py [gemv] [dot] [trsv] [key=value ...]   (key=value -> accblas_tune)
+which = {a for a in sys.argv[1:] if "=" not in a} or {"gemv", "dot", "trsv"}
+for a in sys.argv[1:]:
+    if "=" in a:
+        key, value = a.split("=")
+        ab.tune(key, int(value))
 dev = torch.device("cuda:0")
 h = ab.Handle(0)
 f64, f32, f16 = torch.float64, torch.float32, torch.float16

@@ -59,6 +59,10 @@ for k in sorted(set([0, 1, 2, nb // 4, nb // 2, nb - 2, nb - 1])):
     d = np.diff(t[k, :11])
     print(f"block {k:4d}: " + "  ".join(f"{nm}={int(v)}" for nm, v in zip(names, d)))
 for k in (nb // 2, nb - 1):
+    b5 = t[k, 5]
+    print(f"block {k} tile phase (cycles after the poller's barrier arrival): x in registers "
+          f"+{int(t[k, 32] - b5)}, FMAs done +{int(t[k, 33] - b5)}, row sum written "
+          f"+{int(t[k, 34] - b5)}, barrier passed +{int(t[k, 6] - b5)}")
     base = t[k, 6]
     parts = []
     for step in range(4):
