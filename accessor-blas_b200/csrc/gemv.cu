@@ -646,16 +646,21 @@ int launch_bulk(Handle* h, std::int64_t m, std::int64_t n, Ar alpha,
     auto kernel = gemv_bulk_kernel<St, Ar, ROWS, UNROLL, RG, COLW, STAGES>;
     constexpr size_t smem =
         size_t{RG} * COLW * STAGES * ROWS * kWarp * 16 * UNROLL;
-    static int ctas_per_sm = 0;  // per instantiation
-    if (ctas_per_sm == 0) {
+    // the shared-memory opt-in is per device (and per instantiation)
+    static int per_device[64] = {};
+    int device = 0;
+    ACCBLAS_CUDA(cudaGetDevice(&device));
+    const int slot = (device >= 0 && device < 64) ? device : 0;
+    if (per_device[slot] == 0 || slot != device) {
         ACCBLAS_CUDA(cudaFuncSetAttribute(
             kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
             static_cast<int>(smem)));
         int occ = 0;
         ACCBLAS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
             &occ, kernel, RG * COLW * kWarp, smem));
-        ctas_per_sm = occ > 0 ? occ : 1;
+        per_device[slot] = occ > 0 ? occ : 1;
     }
+    const int ctas_per_sm = per_device[slot];
     const std::int64_t groups = (m + ROWS - 1) / ROWS;
     const std::int64_t items = (groups + RG - 1) / RG;
     int per_sm = tuning().gemv_ctas_per_sm;

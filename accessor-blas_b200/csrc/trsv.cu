@@ -563,12 +563,17 @@ int launch_one(std::int64_t n, const St* A, std::int64_t lda, St* x,
 {
     auto kernel = trsv_kernel<St, Ar, UPPER, UNIT, VECTOR>;
     const size_t smem = sizeof(Ar) * (kB * kLD + 6 * kB);
-    static bool configured = false;  // per instantiation
-    if (!configured) {
+    // the opt-in is per device (and per instantiation)
+    static bool configured[64] = {};
+    int device = 0;
+    ACCBLAS_CUDA(cudaGetDevice(&device));
+    if (device < 0 || device >= 64 || !configured[device]) {
         ACCBLAS_CUDA(cudaFuncSetAttribute(
             kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
             static_cast<int>(smem)));
-        configured = true;
+        if (device >= 0 && device < 64) {
+            configured[device] = true;
+        }
     }
     const std::int64_t nb = (n + kB - 1) / kB;
     kernel<<<static_cast<unsigned>(nb), kThreads, smem, stream>>>(
