@@ -9,19 +9,24 @@
 //   * 128-row block rows, one 512-thread CTA each, ordered by an atomic ticket
 //     (a CTA only ever waits on CTAs that took an earlier ticket, so the
 //     launch cannot deadlock however many CTAs are resident);
-//   * off-diagonal updates done GEMV-style: warp = 8 rows, lane = 4 columns,
-//     wide L1-bypassing loads issued BEFORE the wait for the matching x
-//     block, converted in registers, FMA in the arithmetic type;
+//   * off-diagonal updates done GEMV-style with 4 lanes per row (16
+//     consecutive elements per load instruction and row, full sectors): the
+//     next panel's L1-bypassing loads are in flight while the current one is
+//     consumed, the panel is widened to the arithmetic type BEFORE the wait
+//     for the matching x block, and a row sum needs two shuffle levels;
 //   * progress communicated through the solution itself: solved entries are
 //     published (already rounded through the storage type, as the reference's
 //     accessor write/read does) into a workspace vector that starts out as a
 //     NaN sentinel; consumers poll the values they need with volatile loads, so
 //     one L2 round trip carries both "ready" and the data -- no flag, no
 //     fence, no acquire/release pair on the critical path;
-//   * the diagonal 128x128 tile lives in shared memory; its four 32x32
-//     diagonal sub-blocks are inverted by Gauss-Jordan with all 16 warps
-//     (4 per sub-block) while the CTA would otherwise be waiting, and the
-//     solve walks the sub-blocks left-looking.
+//   * the diagonal 128x128 tile lives in shared memory (leading dimension 136
+//     so 16-byte loads are conflict-free); each of its four 32x32 diagonal
+//     sub-blocks is inverted by one warp, lane j = column j by substitution in
+//     registers, and the solve walks the sub-blocks left-looking;
+//   * the reduction + diagonal-solve code is rehearsed once on scratch data
+//     while the CTA waits, so it is warm in the instruction cache when it
+//     runs for real on the critical path.
 // The last CTA re-arms the workspace (sentinels, ticket) for the next call.
 #include "common.cuh"
 #include "tuning.h"
@@ -38,7 +43,6 @@ constexpr int kNSB = kB / kSB;
 constexpr int kLD = kB + 8;
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / kWarp;
-constexpr int kRowsPerWarp = kB / kWarps;  // 8
 constexpr int kEPL = 4;                    // elements per lane per row
 
 template <typename Ar>
@@ -151,10 +155,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
-__device__ __forceinline__ void group_barrier(int id, int threads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
 // Inverse of one 32x32 triangular sub-block T of D (row-major, leading
 // dimension kLD), in place, by ONE warp: lane j computes column j of T^-1 by
