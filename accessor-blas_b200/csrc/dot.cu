@@ -132,7 +132,7 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     // is only as long as the number of tiles this CTA walks and the error
     // stays below the reference's (thread chains of ~55 at n = 2^28).  fp64
     // arithmetic: one per vector is plenty.
-    constexpr int SLOTS = std::is_same<Ar, float>::value ? VEC : 1;
+    constexpr int SLOTS = std::is_same<Ar, float>::value ? (VEC < 4 ? VEC : 4) : 1;
     Ar acc[UNROLL][SLOTS];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {

@@ -326,8 +326,9 @@ __device__ __forceinline__ void gemv_row_group(
 // short, so the machine drains in a fraction of the time (measured tail of the
 // uniform shape at 16384^2 fp32: 11 us of a 164 us kernel).  The size class is
 // uniform per CTA, so each class runs its own unpredicated instantiation.
-template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW>
-__global__ __launch_bounds__(RG* COLW* kWarp, (ROWS * UNROLL <= 8) ? 3 : 1)
+template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW,
+          int MINB = (ROWS * UNROLL <= 8) ? 3 : 1>
+__global__ __launch_bounds__(RG* COLW* kWarp, MINB)
 void gemv_stream_kernel(
     std::int64_t m, std::int64_t n, Ar alpha, const St* __restrict__ A,
     std::int64_t lda, const St* __restrict__ x, Ar beta, St* __restrict__ y,
@@ -705,12 +706,13 @@ __global__ __launch_bounds__(BLOCK) void gemv_generic_kernel(
     }
 }
 
-template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW>
+template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW,
+          int MINB = (ROWS * UNROLL <= 8) ? 3 : 1>
 int launch_stream(Handle* h, std::int64_t m, std::int64_t n, Ar alpha,
                   const St* A, std::int64_t lda, const St* x, Ar beta, St* y,
                   std::int64_t incy, cudaStream_t stream)
 {
-    auto kernel = gemv_stream_kernel<St, Ar, ROWS, UNROLL, RG, COLW>;
+    auto kernel = gemv_stream_kernel<St, Ar, ROWS, UNROLL, RG, COLW, MINB>;
     static int resident = 0;  // CTAs per SM, per instantiation
     if (resident == 0) {
         int occ = 0;
@@ -816,6 +818,11 @@ int launch_variant(Handle* h, int variant, std::int64_t m, std::int64_t n,
         return launch_stream<St, Ar, 8, UNROLL, 1, 8>(h, m, n, alpha, A, lda, x,
                                                       beta, y, incy, stream);
     default:
+        if (UNROLL == 2 && sizeof(Ar) == 4 && tuning().gemv_occ == 4) {
+            // fp32 arithmetic: 64 registers -> 4 CTAs per SM
+            return launch_stream<St, Ar, 4, UNROLL, 1, 8, 4>(
+                h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+        }
         return launch_stream<St, Ar, 4, UNROLL, 1, 8>(h, m, n, alpha, A, lda, x,
                                                       beta, y, incy, stream);
     }

@@ -97,6 +97,15 @@ __device__ __forceinline__ void pin_register(float& v)
     asm volatile("" : "+f"(v));
 }
 
+__device__ __forceinline__ void named_barrier_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_barrier_arrive(int id, int threads)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 template <typename St>
 struct Quad {
     St v[kEPL];
@@ -454,16 +463,27 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
         }
 
         // ---- diagonal block: the four 32-wide sub-blocks in solve order.
-        //      The 128 threads whose rows are in the current sub-block
-        //      multiply by its inverse; then every later row subtracts the
-        //      new solution entries.
+        //      Warp group g (4 warps = the 128 threads whose rows lie in the
+        //      g-th sub-block to be solved) multiplies by that sub-block's
+        //      inverse and publishes; every later group then subtracts the new
+        //      entries from its own rows.  Synchronisation is by NAMED barriers
+        //      between exactly the warps involved (the solving group only
+        //      arrives and moves on), not by CTA-wide barriers:
+        //        id 1+g : "x of group g is in shared memory"  (group g arrives,
+        //                 later groups wait)          128 * (4 - g) threads
+        //        id 4+g : "rhs of group g is complete" (within group g)  128
+        const int mem_sub = trow >> 5;
+        const int grp = UPPER ? kNSB - 1 - mem_sub : mem_sub;
+        const bool probe = real && trace != nullptr && seg == 0;
 #pragma unroll 1
         for (int step = 0; step < kNSB; ++step) {
-            const int s = UPPER ? kNSB - 1 - step : step;
+            const int s = UPPER ? kNSB - 1 - step : step;  // memory order
             // a thread owns the column pairs 32 s + 2 seg + 8 e + {0, 1}
             const int c2 = s * kSB + 2 * seg;
-            const bool probe = real && trace != nullptr && seg == 0;
-            if ((trow >> 5) == s) {
+            if (grp == step) {
+                if (step > 0) {
+                    named_barrier_sync(4 + step, 4 * kWarp);
+                }
                 if (probe && (trow & 31) == 0) {
                     trace[k * 64 + 16 + 4 * step] = clock64();
                 }
@@ -484,60 +504,58 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                 sol += __shfl_xor_sync(0xffffffffu, sol, 2);
                 if (seg == 0) {
                     // round through storage: later rows see what the
-                    // accessor re-reads.  NOT published here: a global store
-                    // in front of a CTA barrier makes the barrier wait for
-                    // the store's round trip to L2 (~700 cycles per sub-step
-                    // measured); the whole block is published after the loop.
+                    // accessor re-reads
                     const St stored = to_st<St, Ar>(sol);
-                    xsol[trow] = to_ar<Ar, St>(stored);
+                    const Ar back = to_ar<Ar, St>(stored);
+                    xsol[trow] = back;
                     if (probe && (trow & 31) == 0) {
                         trace[k * 64 + 17 + 4 * step] = clock64();
                     }
                 }
-            }
-            __syncthreads();
-            if (step + 1 < kNSB) {
-                const bool later =
-                    UPPER ? ((trow >> 5) < s) : ((trow >> 5) > s);
-                if (later) {
-                    const Pair<Ar>* Drow =
-                        reinterpret_cast<const Pair<Ar>*>(D + trow * kLD + c2);
-                    const Pair<Ar>* xv =
-                        reinterpret_cast<const Pair<Ar>*>(xsol + c2);
-                    Ar p0 = Ar{}, p1 = Ar{};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const Pair<Ar> t = Drow[4 * e];
-                        const Pair<Ar> w = xv[4 * e];
-                        p0 = fma_ar(t.a, w.a, p0);
-                        p1 = fma_ar(t.b, w.b, p1);
-                    }
-                    Ar sum = p0 + p1;
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                    if (seg == 0) {
-                        rhs_cur[trow] -= sum;
-                    }
-                    const int next_s = UPPER ? s - 1 : s + 1;
-                    if (probe && trow == 32 * next_s) {
-                        trace[k * 64 + 18 + 4 * step] = clock64();
+                if (step + 1 < kNSB) {
+                    named_barrier_arrive(1 + step, 4 * kWarp * (kNSB - step));
+                }
+                if (real && seg == 0) {
+                    // publish: progress vector first (the next block row spins
+                    // on it), then the caller's x.  No barrier follows in this
+                    // warp group, so the stores cost nothing here.
+                    const std::int64_t gi = r0 + trow;
+                    if (gi < n) {
+                        const Ar val = xsol[trow];
+                        st_volatile(xs + gi, Sentinel<Ar>::clean(val));
+                        x[gi * incx] = to_st<St, Ar>(val);
                     }
                 }
-                __syncthreads();
-            }
-            if (real) {
-                ACCBLAS_TRACE(7 + step, clock64());
+            } else if (grp > step) {
+                named_barrier_sync(1 + step, 4 * kWarp * (kNSB - step));
+                const Pair<Ar>* Drow =
+                    reinterpret_cast<const Pair<Ar>*>(D + trow * kLD + c2);
+                const Pair<Ar>* xv =
+                    reinterpret_cast<const Pair<Ar>*>(xsol + c2);
+                Ar p0 = Ar{}, p1 = Ar{};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const Pair<Ar> t = Drow[4 * e];
+                    const Pair<Ar> w = xv[4 * e];
+                    p0 = fma_ar(t.a, w.a, p0);
+                    p1 = fma_ar(t.b, w.b, p1);
+                }
+                Ar sum = p0 + p1;
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                if (seg == 0) {
+                    rhs_cur[trow] -= sum;
+                }
+                if (probe && grp == step + 1 && (trow & 31) == 0) {
+                    trace[k * 64 + 18 + 4 * step] = clock64();
+                }
             }
         }
-        if (real && seg == 0) {
-            // publish the solved block: progress vector first (that is what
-            // the next block row is spinning on), then the caller's x
-            const std::int64_t gi = r0 + trow;
-            if (gi < n) {
-                const Ar val = xsol[trow];
-                st_volatile(xs + gi, Sentinel<Ar>::clean(val));
-                x[gi * incx] = to_st<St, Ar>(val);
-            }
+        // both passes end with the whole CTA in step (the rehearsal must not
+        // run into the real pass's barriers)
+        __syncthreads();
+        if (real) {
+            ACCBLAS_TRACE(10, clock64());
         }
     }
     ACCBLAS_TRACE(12, static_cast<long long>(globaltimer_ns()));

@@ -51,12 +51,11 @@ for it in range(3):
     assert rc == 0
     print(f"run {it}: {e0.elapsed_time(e1) * 1e3:.1f} us total")
 t = trace.cpu().numpy().reshape(nb, 64)
-names = ["load diag", "invert", "(wait) ->issue last", "poll last x", "release", "tile+reduce",
-         "sub0", "sub1", "sub2", "sub3"]
+names = ["load diag", "invert", "(wait) ->issue last", "poll last x", "release", "tile+reduce"]
 for k in sorted(set([0, 1, 2, nb // 4, nb // 2, nb - 2, nb - 1])):
     if k < 0 or k >= nb:
         continue
-    d = np.diff(t[k, :11])
+    d = np.diff(t[k, :7])
     print(f"block {k:4d}: " + "  ".join(f"{nm}={int(v)}" for nm, v in zip(names, d)))
 for k in (nb // 2, nb - 1):
     b5 = t[k, 5]

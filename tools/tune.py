@@ -53,19 +53,28 @@ if "gemv" in which:
         h.fill_uniform(m, k, A, k, 42, 0)
         h.fill_uniform(k, 1, x, 1, 42, m * k)
         for ar in (torch.float64, torch.float32):
-            for unroll, variant, stages in itertools.product((1, 2), (4, 5, 6), (0, 2, 3, 4)):
+            for unroll, variant, stages, occ, taper in [(2, 4, 0, 3, 1), (2, 4, 0, 4, 1), (2, 4, 0, 3, 0),
+                                                         (2, 5, 0, 3, 1), (2, 2, 0, 3, 1), (2, 3, 0, 3, 1),
+                                                         (2, 4, 0, 3, 1), (2, 4, 0, 4, 1)]:
                 ab.tune("gemv_unroll", unroll)
                 ab.tune("gemv_variant", variant)
                 ab.tune("gemv_stages", stages)
+                ab.tune("gemv_occ", occ)
+                ab.tune("gemv_taper", taper)
                 ms = min_of_10(lambda: h.gemv(ar, m, k, 1.0, A, k, x, 1, 0.0, y, 1), torch)
                 gbs = gemv_bytes(m, k, A.element_size()) / ms / 1e6
-                key = f"gemv Acc<{NAME[ar]},{NAME[st]}> unroll={unroll} variant={variant} stages={stages}"
+                key = (f"gemv Acc<{NAME[ar]},{NAME[st]}> unroll={unroll} variant={variant} "
+                       f"stages={stages} occ={occ} taper={taper}")
+                if key in results:
+                    key += " (repeat)"
                 results[key] = round(gbs, 1)
                 print(key, f"{gbs:8.1f} GB/s", flush=True)
         del A
     ab.tune("gemv_unroll", 2)
     ab.tune("gemv_variant", 0)
     ab.tune("gemv_stages", 0)
+    ab.tune("gemv_occ", 3)
+    ab.tune("gemv_taper", 1)
 
 out = ROOT / "gpurun_out"
 out.mkdir(exist_ok=True)
