@@ -575,8 +575,10 @@ int accblas_tune(const char* key, int value)
         t.gemv_stages = value;
     } else if (!strcmp(key, "gemv_taper")) {
         t.gemv_taper = value;
-    } else if (!strcmp(key, "gemv_occ")) {
-        t.gemv_occ = value;
+    } else if (!strcmp(key, "gemv_pipe")) {
+        t.gemv_pipe = value;
+    } else if (!strcmp(key, "gemv_intwords")) {
+        t.gemv_intwords = value;
     } else if (!strcmp(key, "trsv_variant")) {
         t.trsv_variant = value;
     } else {

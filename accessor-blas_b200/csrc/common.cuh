@@ -142,7 +142,10 @@ __device__ __forceinline__ float to_ar<float, __half>(__half v)
 template <>
 __device__ __forceinline__ double to_ar<double, __half>(__half v)
 {
-    return static_cast<double>(__half2float(v));
+    // one F2F.F64.F16 (exact) instead of half -> float -> double
+    double d;
+    asm("cvt.f64.f16 %0, %1;" : "=d"(d) : "h"(__half_as_ushort(v)));
+    return d;
 }
 
 // arithmetic -> storage: ONE round-to-nearest-even
@@ -192,6 +195,16 @@ __device__ __forceinline__ uint4 ldg_stream_128(const void* p)
 __device__ __forceinline__ uint4 ldg_cached_128(const void* p)
 {
     return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+// same, as a volatile asm so that it keeps its place among the streaming loads
+__device__ __forceinline__ uint4 ldg_cached_128_ordered(const void* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
 }
 
 // number of St elements in one 128-bit vector

@@ -63,24 +63,36 @@ __device__ __forceinline__ unsigned long long gemv_globaltimer()
 // Inf/NaN halves (exponent 31) do NOT map correctly; they are detected on the
 // otherwise idle fp16 pipe (0 * h is NaN exactly for those) and the warp
 // recomputes its part with ordinary conversions.
-// Two shifts and a mask per element on the integer pipe instead of one F2F on
-// the quarter-rate pipe.
+// Three integer instructions per element instead of one F2F on the
+// quarter-rate pipe: isolate the half in the top 16 bits of a word (LOP3 or a
+// shift), one signed 32x32->64 multiply by 2^26 (IMAD.WIDE: high word = the
+// word shifted right by 6 with the sign replicated, low word = 0 -- the
+// register PAIR a double needs comes out of one instruction; building it from
+// a 32-bit shift costs an extra "move zero into the low register" per
+// element), and one mask on the high word.
 // ---------------------------------------------------------------------------
 struct HalfToDoubleScaled {
-    static constexpr unsigned kMask = 0x81FFFC00u;
+    static constexpr long long kMask =
+        static_cast<long long>(0x81FFFC00FFFFFFFFull);
     // 2^1008 as a double: exponent field 1008 + 1023 = 2031
     static __device__ __forceinline__ double scale()
     {
         return __hiloint2double(2031 << 20, 0);
     }
+    // t holds the half in bits [31:16] and zeros below
+    static __device__ __forceinline__ double widen_top(unsigned t)
+    {
+        long long p;
+        asm("mul.wide.s32 %0, %1, 0x4000000;" : "=l"(p) : "r"(t));
+        return __longlong_as_double(p & kMask);
+    }
     static __device__ __forceinline__ double low(unsigned w)
     {
-        const int v = static_cast<int>(w << 16);
-        return __hiloint2double((v >> 6) & kMask, 0);
+        return widen_top(w << 16);
     }
     static __device__ __forceinline__ double high(unsigned w)
     {
-        return __hiloint2double((static_cast<int>(w) >> 6) & kMask, 0);
+        return widen_top(w & 0xFFFF0000u);
     }
 };
 
@@ -200,6 +212,266 @@ struct ChunkOps {
     }
 };
 
+// fp16 -> fp64 on the conversion pipe in ONE instruction (F2F.F64.F16 with a
+// half selector; `static_cast<double>(__half2float(h))` costs two)
+__device__ __forceinline__ double half_bits_to_double(unsigned short bits)
+{
+    double d;
+    asm("cvt.f64.f16 %0, %1;" : "=d"(d) : "h"(bits));
+    return d;
+}
+
+// One "batch" = one 128-bit vector per lane from each of the ROWS rows plus the
+// matching vector of x: 32 * VEC consecutive columns.  The streaming loop keeps
+// one batch in flight while the previous one is being consumed (software
+// pipeline of depth 2 in registers), so a warp always has ROWS * 512 bytes of
+// the matrix stream outstanding -- also while it converts and multiplies.
+// ncu on the unpipelined loop: "long scoreboard" was 4.8 of every 7.9 stall
+// cycles of Acc<fp64,fp16>, issue slots 56 % busy, DRAM 66 %.
+template <typename Ar, typename St, int ROWS, bool FAST, int IW>
+struct BatchOps {
+    static constexpr int VEC = vec_traits<St>::elems;
+    static constexpr int COLS = kWarp * VEC;
+    static constexpr int SPLIT = std::is_same<Ar, float>::value ? 2 : 1;
+    static constexpr int SLOTS = 2 * SPLIT;
+    // FAST (fp16 storage, fp64 arithmetic): words [0, kIntWords) of a vector
+    // are widened on the integer pipes (HalfToDoubleScaled), the remaining
+    // words on the conversion pipe, so that neither path has to carry the
+    // whole stream: the conversion pipe handles 16 elements/clk/SM, the HBM
+    // stream delivers ~14.
+    static constexpr int kIntWords = IW;
+
+    struct Batch {
+        uint4 x;
+        uint4 a[ROWS];
+    };
+
+    // Orders the consumption of `b` after every volatile load issued so far
+    // (volatile asm statements keep their program order); without it the
+    // compiler sinks the next batch's loads below the current batch's
+    // arithmetic to save registers, which undoes the pipeline.
+    static __device__ __forceinline__ void pin(Batch& b)
+    {
+        asm volatile("" : "+r"(b.x.x), "+r"(b.x.y), "+r"(b.x.z), "+r"(b.x.w));
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            asm volatile(""
+                         : "+r"(b.a[r].x), "+r"(b.a[r].y), "+r"(b.a[r].z),
+                           "+r"(b.a[r].w));
+        }
+    }
+
+    // `col` = first column of this lane's vector
+    static __device__ __forceinline__ void load(const St* const (&row)[ROWS],
+                                                const St* __restrict__ x,
+                                                std::int64_t col, Batch& b)
+    {
+        b.x = ldg_cached_128_ordered(x + col);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            b.a[r] = ldg_stream_128(row[r] + col);
+        }
+    }
+
+    template <int PARITY>
+    static __device__ __forceinline__ void compute(const Batch& b,
+                                                   Ar (&acc)[ROWS][SLOTS],
+                                                   __half2& chk)
+    {
+        if constexpr (FAST) {
+            const unsigned xw[4] = {b.x.x, b.x.y, b.x.z, b.x.w};
+            double xv[VEC];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                xv[2 * j] = half_bits_to_double(
+                    static_cast<unsigned short>(xw[j] & 0xffffu));
+                xv[2 * j + 1] =
+                    half_bits_to_double(static_cast<unsigned short>(xw[j] >> 16));
+            }
+            const double s = HalfToDoubleScaled::scale();
+#pragma unroll
+            for (int i = 0; i < 2 * kIntWords; ++i) {
+                xv[i] = xv[i] * s;
+            }
+            const __half2 zero = __float2half2_rn(0.0f);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const unsigned w[4] = {b.a[r].x, b.a[r].y, b.a[r].z, b.a[r].w};
+                Ar& t = acc[r][PARITY];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j < kIntWords) {
+                        t = fma(HalfToDoubleScaled::low(w[j]), xv[2 * j], t);
+                        t = fma(HalfToDoubleScaled::high(w[j]), xv[2 * j + 1], t);
+                        chk = __hfma2(*reinterpret_cast<const __half2*>(&w[j]),
+                                      zero, chk);
+                    } else {
+                        t = fma(half_bits_to_double(static_cast<unsigned short>(
+                                    w[j] & 0xffffu)),
+                                xv[2 * j], t);
+                        t = fma(half_bits_to_double(
+                                    static_cast<unsigned short>(w[j] >> 16)),
+                                xv[2 * j + 1], t);
+                    }
+                }
+            }
+        } else {
+            Ar xv[VEC];
+            unpack_all<Ar, St>(b.x, xv);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    Ar& t = acc[r][PARITY * SPLIT + (i % SPLIT)];
+                    t = fma_ar(unpack<Ar>(b.a[r], i, St{}), xv[i], t);
+                }
+            }
+        }
+    }
+
+    // all full chunks (= pairs of batches) cw, cw + COLW, ... of the row group
+    template <int COLW>
+    static __device__ __forceinline__ void stream(
+        const St* const (&row)[ROWS], const St* __restrict__ x,
+        std::int64_t full_chunks, int cw, int lane, Ar (&acc)[ROWS][SLOTS],
+        __half2& chk)
+    {
+        constexpr std::int64_t CHUNK = 2 * COLS;
+        const std::int64_t lane_col = static_cast<std::int64_t>(lane) * VEC;
+        std::int64_t k = cw;
+        if (k >= full_chunks) {
+            return;
+        }
+        Batch b0, b1;
+        load(row, x, k * CHUNK + lane_col, b0);
+        for (;;) {
+            load(row, x, k * CHUNK + COLS + lane_col, b1);
+            pin(b0);  // the loads above are issued BEFORE b0 is consumed
+            compute<0>(b0, acc, chk);
+            k += COLW;
+            const bool more = k < full_chunks;
+            if (more) {
+                load(row, x, k * CHUNK + lane_col, b0);
+            }
+            pin(b1);
+            compute<1>(b1, acc, chk);
+            if (!more) {
+                break;
+            }
+        }
+    }
+};
+
+// Same batches, but the stream lands in shared memory: every lane copies the
+// 16 bytes per row (and of x) that it will consume ITSELF with cp.async
+// (LDGSTS, L1-bypassing for the matrix) into its own slots of a per-warp ring,
+// so "has my data arrived" is a per-thread cp.async.wait_group -- no barrier,
+// no mbarrier, no producer lane -- and the bytes in flight per warp are
+// (STAGES - 1) x (ROWS + 1) x 512, independent of the register budget.
+template <typename Ar, typename St, int ROWS, bool FAST, int IW, int STAGES>
+struct AsyncOps {
+    using B = BatchOps<Ar, St, ROWS, FAST, IW>;
+    static constexpr int VEC = B::VEC;
+    static constexpr int COLS = B::COLS;
+    static constexpr unsigned STAGE_BYTES = (ROWS + 1) * 512;
+
+    static __device__ __forceinline__ void copy16_stream(unsigned dst,
+                                                         const void* src)
+    {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                     "l"(src)
+                     : "memory");
+    }
+    static __device__ __forceinline__ void copy16_cached(unsigned dst,
+                                                         const void* src)
+    {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst),
+                     "l"(src)
+                     : "memory");
+    }
+    static __device__ __forceinline__ void commit()
+    {
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    static __device__ __forceinline__ void wait_oldest()
+    {
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+    }
+    static __device__ __forceinline__ uint4 lds(unsigned addr)
+    {
+        uint4 r;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                     : "r"(addr));
+        return r;
+    }
+
+    // `ring` = shared address of this LANE's 16 bytes in stage 0, row slot 0
+    template <int COLW>
+    static __device__ __forceinline__ void stream(
+        const St* const (&row)[ROWS], const St* __restrict__ x,
+        std::int64_t full_chunks, int cw, int lane,
+        Ar (&acc)[ROWS][B::SLOTS], __half2& chk, unsigned ring)
+    {
+        constexpr std::int64_t CHUNK = 2 * COLS;
+        const std::int64_t count =
+            full_chunks > cw ? (full_chunks - cw + COLW - 1) / COLW : 0;
+        const std::int64_t nb = 2 * count;  // batches of this warp
+        const std::int64_t lane_col = static_cast<std::int64_t>(lane) * VEC;
+        auto issue = [&](std::int64_t j, int slot) {
+            const std::int64_t col =
+                (cw + (j >> 1) * COLW) * CHUNK + (j & 1) * COLS + lane_col;
+            const unsigned dst = ring + slot * STAGE_BYTES;
+            copy16_cached(dst, x + col);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                copy16_stream(dst + (r + 1) * 512, row[r] + col);
+            }
+        };
+        auto fetch = [&](int slot, typename B::Batch& b) {
+            const unsigned src = ring + slot * STAGE_BYTES;
+            b.x = lds(src);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                b.a[r] = lds(src + (r + 1) * 512);
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) {
+            if (s < nb) {
+                issue(s, s);
+            }
+            commit();
+        }
+        int slot = 0;               // stage holding batch j
+        int refill = STAGES - 1;    // stage batch j + STAGES - 1 goes to
+        for (std::int64_t j = 0; j < nb; j += 2) {
+            typename B::Batch b;
+            wait_oldest();
+            fetch(slot, b);
+            if (j + STAGES - 1 < nb) {
+                issue(j + STAGES - 1, refill);
+            }
+            commit();
+            B::template compute<0>(b, acc, chk);
+            slot = (slot + 1 == STAGES) ? 0 : slot + 1;
+            refill = (refill + 1 == STAGES) ? 0 : refill + 1;
+
+            wait_oldest();
+            fetch(slot, b);
+            if (j + STAGES < nb) {
+                issue(j + STAGES, refill);
+            }
+            commit();
+            B::template compute<1>(b, acc, chk);
+            slot = (slot + 1 == STAGES) ? 0 : slot + 1;
+            refill = (refill + 1 == STAGES) ? 0 : refill + 1;
+        }
+        // nothing may still be landing in the ring when the CTA moves on
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+};
+
 // alpha * sum (+ beta * y), rounded to storage
 template <typename Ar, typename St>
 __device__ __forceinline__ void write_row(St* y, std::int64_t idx, Ar alpha,
@@ -216,12 +488,13 @@ __device__ __forceinline__ void write_row(St* y, std::int64_t idx, Ar alpha,
 
 // One row group of R rows: the COLW warps that share it walk the column chunks,
 // reduce and write.  `part` is the CTA's [RG][COLW][MAXR] staging array.
-template <typename St, typename Ar, int R, int MAXR, int UNROLL, int COLW>
+template <typename St, typename Ar, int R, int MAXR, int UNROLL, int COLW,
+          int PIPE, int IW>
 __device__ __forceinline__ void gemv_row_group(
     std::int64_t m, std::int64_t n, Ar alpha, const St* __restrict__ A,
     std::int64_t lda, const St* __restrict__ x, Ar beta, St* __restrict__ y,
     std::int64_t incy, std::int64_t row0, int rg, int cw, int lane,
-    Ar (*part)[COLW][MAXR])
+    Ar (*part)[COLW][MAXR], unsigned ring)
 {
     constexpr bool FAST = use_scaled_half<Ar, St>::value;
     using Ops = ChunkOps<Ar, St, R, UNROLL, FAST>;
@@ -252,8 +525,18 @@ __device__ __forceinline__ void gemv_row_group(
         }
         const std::int64_t full_chunks = n / CHUNK;
         __half2 chk = __float2half2_rn(0.0f);
-        for (std::int64_t k = cw; k < full_chunks; k += COLW) {
-            Ops::full(row, x, k * CHUNK, lane, part_acc, chk);
+        if constexpr (PIPE >= 2 && UNROLL == 2) {
+            AsyncOps<Ar, St, R, FAST, IW, PIPE>::template stream<COLW>(
+                row, x, full_chunks, cw, lane, part_acc, chk, ring);
+        } else if constexpr (PIPE == 1 && UNROLL == 2) {
+            // same chunk ownership and the same accumulator per (row, vector
+            // slot) as the unpipelined loop: results are bit-identical
+            BatchOps<Ar, St, R, FAST, IW>::template stream<COLW>(
+                row, x, full_chunks, cw, lane, part_acc, chk);
+        } else {
+            for (std::int64_t k = cw; k < full_chunks; k += COLW) {
+                Ops::full(row, x, k * CHUNK, lane, part_acc, chk);
+            }
         }
         if (FAST) {
             // a non-finite half went through the scaled path: redo this
@@ -327,7 +610,7 @@ __device__ __forceinline__ void gemv_row_group(
 // uniform shape at 16384^2 fp32: 11 us of a 164 us kernel).  The size class is
 // uniform per CTA, so each class runs its own unpredicated instantiation.
 template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW,
-          int MINB = (ROWS * UNROLL <= 8) ? 3 : 1>
+          int MINB = (ROWS * UNROLL <= 8) ? 3 : 1, int PIPE = 0, int IW = 2>
 __global__ __launch_bounds__(RG* COLW* kWarp, MINB)
 void gemv_stream_kernel(
     std::int64_t m, std::int64_t n, Ar alpha, const St* __restrict__ A,
@@ -337,10 +620,16 @@ void gemv_stream_kernel(
     constexpr int HALF = ROWS >= 2 ? ROWS / 2 : 1;
     constexpr int QUARTER = ROWS >= 4 ? ROWS / 4 : 1;
     __shared__ Ar part[RG][COLW][ROWS];
+    extern __shared__ __align__(128) unsigned char gemv_ring[];
     const int lane = threadIdx.x & (kWarp - 1);
     const int warp = threadIdx.x >> 5;
     const int rg = warp / COLW;  // row group inside the CTA
     const int cw = warp % COLW;  // column slot inside the row group
+    // cp.async ring of this warp (PIPE >= 2): PIPE stages of (ROWS + 1) x 512 B
+    const unsigned ring =
+        PIPE >= 2 ? static_cast<unsigned>(__cvta_generic_to_shared(gemv_ring)) +
+                        warp * (PIPE * (ROWS + 1) * 512) + lane * 16
+                  : 0u;
     unsigned long long* const trace = g_gemv_trace;
     if (trace != nullptr && threadIdx.x == 0) {
         unsigned smid;
@@ -352,18 +641,18 @@ void gemv_stream_kernel(
     const std::int64_t b = blockIdx.x;
     if (b < b_full) {
         const std::int64_t row0 = (b * RG + rg) * ROWS;
-        gemv_row_group<St, Ar, ROWS, ROWS, UNROLL, COLW>(
-            m, n, alpha, A, lda, x, beta, y, incy, row0, rg, cw, lane, part);
+        gemv_row_group<St, Ar, ROWS, ROWS, UNROLL, COLW, PIPE, IW>(
+            m, n, alpha, A, lda, x, beta, y, incy, row0, rg, cw, lane, part, ring);
     } else if (b < b_full + b_half) {
         const std::int64_t row0 =
             b_full * RG * ROWS + ((b - b_full) * RG + rg) * HALF;
-        gemv_row_group<St, Ar, HALF, ROWS, UNROLL, COLW>(
-            m, n, alpha, A, lda, x, beta, y, incy, row0, rg, cw, lane, part);
+        gemv_row_group<St, Ar, HALF, ROWS, UNROLL, COLW, PIPE, IW>(
+            m, n, alpha, A, lda, x, beta, y, incy, row0, rg, cw, lane, part, ring);
     } else {
         const std::int64_t row0 = b_full * RG * ROWS + b_half * RG * HALF +
                                   ((b - b_full - b_half) * RG + rg) * QUARTER;
-        gemv_row_group<St, Ar, QUARTER, ROWS, UNROLL, COLW>(
-            m, n, alpha, A, lda, x, beta, y, incy, row0, rg, cw, lane, part);
+        gemv_row_group<St, Ar, QUARTER, ROWS, UNROLL, COLW, PIPE, IW>(
+            m, n, alpha, A, lda, x, beta, y, incy, row0, rg, cw, lane, part, ring);
     }
     if (trace != nullptr && threadIdx.x == 0) {
         trace[3 * blockIdx.x + 1] = gemv_globaltimer();
@@ -707,19 +996,30 @@ __global__ __launch_bounds__(BLOCK) void gemv_generic_kernel(
 }
 
 template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW,
-          int MINB = (ROWS * UNROLL <= 8) ? 3 : 1>
+          int MINB = (ROWS * UNROLL <= 8) ? 3 : 1, int PIPE = 0, int IW = 2>
 int launch_stream(Handle* h, std::int64_t m, std::int64_t n, Ar alpha,
                   const St* A, std::int64_t lda, const St* x, Ar beta, St* y,
                   std::int64_t incy, cudaStream_t stream)
 {
-    auto kernel = gemv_stream_kernel<St, Ar, ROWS, UNROLL, RG, COLW, MINB>;
-    static int resident = 0;  // CTAs per SM, per instantiation
-    if (resident == 0) {
+    auto kernel = gemv_stream_kernel<St, Ar, ROWS, UNROLL, RG, COLW, MINB, PIPE, IW>;
+    constexpr size_t smem =
+        PIPE >= 2 ? size_t{RG} * COLW * PIPE * (ROWS + 1) * 512 : 0;
+    static int resident_on[64] = {};  // CTAs per SM, per instantiation and device
+    int device = 0;
+    ACCBLAS_CUDA(cudaGetDevice(&device));
+    const int slot = (device >= 0 && device < 64) ? device : 0;
+    if (resident_on[slot] == 0 || slot != device) {
+        if (smem > 0) {
+            ACCBLAS_CUDA(cudaFuncSetAttribute(
+                kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                static_cast<int>(smem)));
+        }
         int occ = 0;
         ACCBLAS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &occ, kernel, RG * COLW * kWarp, 0));
-        resident = occ > 0 ? occ : 1;
+            &occ, kernel, RG * COLW * kWarp, smem));
+        resident_on[slot] = occ > 0 ? occ : 1;
     }
+    const int resident = resident_on[slot];
     // taper: the last two "waves" of CTAs own half / a quarter of the rows
     constexpr int HALF = ROWS >= 2 ? ROWS / 2 : 1;
     constexpr int QUARTER = ROWS >= 4 ? ROWS / 4 : 1;
@@ -739,93 +1039,96 @@ int launch_stream(Handle* h, std::int64_t m, std::int64_t n, Ar alpha,
         set_error("gemv: too many rows (%lld)", static_cast<long long>(m));
         return ACCBLAS_ERR_INVALID;
     }
-    kernel<<<static_cast<unsigned>(grid), RG * COLW * kWarp, 0, stream>>>(
+    kernel<<<static_cast<unsigned>(grid), RG * COLW * kWarp, smem, stream>>>(
         m, n, alpha, A, lda, x, beta, y, incy, b_full, b_half);
     ACCBLAS_CUDA(cudaGetLastError());
     return ACCBLAS_OK;
 }
 
-// variant: 1 = warp owns 4 whole rows (8 groups per CTA)
-//          2 = CTA owns 2 rows, 8 warps split the columns
+// variant: 2 = CTA owns 2 rows, 8 warps split the columns
 //          3 = CTA owns 1 row,  8 warps split the columns
-//          4 = CTA owns 4 rows, 8 warps split the columns
+//          4 = CTA owns 4 rows, 8 warps split the columns (default shape)
 //          5 = CTA owns 8 rows (2 groups of 4), 4 warps per group
-//          6 = CTA owns 16 rows (4 groups of 4), 2 warps per group
-//          7 = CTA owns 8 rows (1 group of 8), 8 warps split the columns
-template <typename St, typename Ar, int UNROLL, int RG, int COLW>
-int launch_bulk_stages(Handle* h, int stages, std::int64_t m, std::int64_t n,
-                       Ar alpha,
-                       const St* A, std::int64_t lda, const St* x, Ar beta,
-                       St* y, std::int64_t incy, cudaStream_t stream)
-{
-    switch (stages) {
-    case 2:
-        return launch_bulk<St, Ar, 4, UNROLL, RG, COLW, 2>(
-            h, m, n, alpha, A, lda, x, beta, y, incy, stream);
-    case 4:
-        return launch_bulk<St, Ar, 4, UNROLL, RG, COLW, 4>(
-            h, m, n, alpha, A, lda, x, beta, y, incy, stream);
-    default:
-        return launch_bulk<St, Ar, 4, UNROLL, RG, COLW, 3>(
-            h, m, n, alpha, A, lda, x, beta, y, incy, stream);
-    }
-}
-
+// (shapes that lost everywhere on B200 -- a warp owning whole rows, 16-row
+// CTAs, 8-row groups -- are gone; profiles/r01_summary.md has their numbers)
 template <typename St, typename Ar, int UNROLL>
 int launch_variant(Handle* h, int variant, std::int64_t m, std::int64_t n,
                    Ar alpha,
                    const St* A, std::int64_t lda, const St* x, Ar beta, St* y,
                    std::int64_t incy, cudaStream_t stream)
 {
-    const int stages = tuning().gemv_stages;
-    if (stages > 0 && UNROLL <= 2) {
-        // bulk-copy pipeline: 4-row groups, 8 / 4 / 2 warps per group
-        constexpr int U = UNROLL <= 2 ? UNROLL : 2;
-        switch (variant) {
-        case 5:
-            return launch_bulk_stages<St, Ar, U, 2, 4>(h, stages, m, n, alpha, A,
-                                                       lda, x, beta, y, incy,
-                                                       stream);
-        case 6:
-            return launch_bulk_stages<St, Ar, U, 4, 2>(h, stages, m, n, alpha, A,
-                                                       lda, x, beta, y, incy,
-                                                       stream);
+    constexpr bool FAST = use_scaled_half<Ar, St>::value;
+    if constexpr (UNROLL == 2) {
+        // bulk-copy pipeline (default shape only): ring depth 2 / 3 / 4
+        switch (variant == 4 ? tuning().gemv_stages : 0) {
+        case 2:
+            return launch_bulk<St, Ar, 4, 2, 1, 8, 2>(h, m, n, alpha, A, lda, x,
+                                                      beta, y, incy, stream);
+        case 3:
+            return launch_bulk<St, Ar, 4, 2, 1, 8, 3>(h, m, n, alpha, A, lda, x,
+                                                      beta, y, incy, stream);
         case 4:
-            return launch_bulk_stages<St, Ar, U, 1, 8>(h, stages, m, n, alpha, A,
-                                                       lda, x, beta, y, incy,
-                                                       stream);
+            return launch_bulk<St, Ar, 4, 2, 1, 8, 4>(h, m, n, alpha, A, lda, x,
+                                                      beta, y, incy, stream);
+        default:
+            break;
+        }
+        switch (variant) {
+        case 2:
+            return launch_stream<St, Ar, 2, 2, 1, 8>(h, m, n, alpha, A, lda, x,
+                                                     beta, y, incy, stream);
+        case 5:
+            return launch_stream<St, Ar, 4, 2, 2, 4>(h, m, n, alpha, A, lda, x,
+                                                     beta, y, incy, stream);
         default:
             break;
         }
     }
-    switch (variant) {
-    case 1:
-        return launch_stream<St, Ar, 4, UNROLL, 8, 1>(h, m, n, alpha, A, lda, x,
-                                                      beta, y, incy, stream);
-    case 2:
-        return launch_stream<St, Ar, 2, UNROLL, 1, 8>(h, m, n, alpha, A, lda, x,
-                                                      beta, y, incy, stream);
-    case 3:
+    if (variant == 3) {
         return launch_stream<St, Ar, 1, UNROLL, 1, 8>(h, m, n, alpha, A, lda, x,
                                                       beta, y, incy, stream);
-    case 5:
-        return launch_stream<St, Ar, 4, UNROLL, 2, 4>(h, m, n, alpha, A, lda, x,
-                                                      beta, y, incy, stream);
-    case 6:
-        return launch_stream<St, Ar, 4, UNROLL, 4, 2>(h, m, n, alpha, A, lda, x,
-                                                      beta, y, incy, stream);
-    case 7:
-        return launch_stream<St, Ar, 8, UNROLL, 1, 8>(h, m, n, alpha, A, lda, x,
-                                                      beta, y, incy, stream);
-    default:
-        if (UNROLL == 2 && sizeof(Ar) == 4 && tuning().gemv_occ == 4) {
-            // fp32 arithmetic: 64 registers -> 4 CTAs per SM
-            return launch_stream<St, Ar, 4, UNROLL, 1, 8, 4>(
+    }
+    if constexpr (UNROLL == 2) {
+        int pipe = tuning().gemv_pipe;
+        if (pipe < 0) {
+            // measured on B200 (same box, min of 10): keeping one batch in
+            // flight while the previous is consumed gains 5-7 % for
+            // Acc<fp64,fp16> (instruction-heavy) and loses 1-8 % elsewhere
+            pipe = FAST ? 1 : 0;
+        }
+        if (pipe == 3) {
+            return launch_stream<St, Ar, 4, 2, 1, 8, 3, 3>(
                 h, m, n, alpha, A, lda, x, beta, y, incy, stream);
         }
-        return launch_stream<St, Ar, 4, UNROLL, 1, 8>(h, m, n, alpha, A, lda, x,
-                                                      beta, y, incy, stream);
+        if (pipe == 4) {
+            return launch_stream<St, Ar, 4, 2, 1, 8, 2, 4>(
+                h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+        }
+        if (pipe != 0) {
+            if constexpr (FAST) {
+                switch (tuning().gemv_intwords) {
+                case 0:
+                    return launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 0>(
+                        h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+                case 1:
+                    return launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 1>(
+                        h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+                case 3:
+                    return launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 3>(
+                        h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+                case 4:
+                    return launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 4>(
+                        h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+                default:
+                    break;
+                }
+            }
+            return launch_stream<St, Ar, 4, 2, 1, 8, 3, 1>(
+                h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+        }
     }
+    return launch_stream<St, Ar, 4, UNROLL, 1, 8>(h, m, n, alpha, A, lda, x,
+                                                  beta, y, incy, stream);
 }
 
 template <typename St, typename Ar>

@@ -11,7 +11,8 @@ struct Tuning {
     int gemv_unroll = 2;       // vectors per row in flight per lane
     int gemv_variant = 0;      // 0 = auto, 1 = warp-per-4-rows, 2 = CTA-per-2-rows, 3 = CTA-per-row
     int gemv_ctas_per_sm = 0;  // 0 = all row groups as separate CTAs
-    int gemv_occ = 3;          // CTAs per SM the default fp32-arithmetic GEMV is compiled for (3 or 4)
+    int gemv_pipe = -1;        // software-pipelined batches in the default GEMV shape: -1 = per pair, 0 / 1
+    int gemv_intwords = 2;     // Acc<fp64,fp16>: words per 128-bit vector widened on the integer pipes (rest: F2F)
     int gemv_taper = 1;        // shorter row groups at the end of the grid
     int gemv_stages = 0;       // 0 = register path, 2..4 = bulk-copy ring depth
     int trsv_variant = 0;      // 0 = default

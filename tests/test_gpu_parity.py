@@ -382,6 +382,34 @@ def test_gemv_all_launch_shapes(oracle, ab, handle, variant, stages):
         ab.tune("gemv_unroll", 2)
 
 
+@pytest.mark.parametrize("pipe", [0, 1, 3, 4])
+def test_gemv_pipelined_streams_are_bit_identical(oracle, ab, handle, pipe):
+    """The register-pipelined (1) and cp.async-ring (3, 4 stages) streaming
+    loops own the same chunks and use the same accumulators as the plain loop
+    (0): results must be bit-identical, for every pair, incl. ragged edges."""
+    shapes = [(515, 1030, 1032), (37, 4100, 4104), (1000, 8192, 8192), (5, 16384, 16384)]
+    try:
+        for m, n, lda in shapes:
+            for ar, st in ((torch.float64, torch.float32), (torch.float64, torch.float16),
+                           (torch.float32, torch.float16), (torch.float64, torch.float64),
+                           (torch.float32, torch.float32), (torch.float32, torch.float64)):
+                A = stored(oracle, m * lda, st)
+                x = stored(oracle, n, st, first=m * lda)
+                y = stored(oracle, m, st, first=m * lda + n)
+                ab.tune("gemv_variant", 4)
+                ab.tune("gemv_pipe", 0)
+                want = run_gemv(handle, ar, A, m, n, lda, x, 1.0, 1.0, y)
+                ab.tune("gemv_pipe", pipe)
+                for iw in ((0, 1, 2, 3, 4) if pipe == 1 and st == torch.float16 and ar == torch.float64 else (3,)):
+                    ab.tune("gemv_intwords", iw)
+                    got = run_gemv(handle, ar, A, m, n, lda, x, 1.0, 1.0, y)
+                    assert np.array_equal(got, want), (pipe, iw, m, n, ar, st)
+    finally:
+        ab.tune("gemv_variant", 0)
+        ab.tune("gemv_pipe", -1)
+        ab.tune("gemv_intwords", 2)
+
+
 def test_gemv_fp16_fp64_fast_path_is_bit_identical_and_handles_non_finite(oracle, handle):
     """The integer widening used for Acc<fp64,fp16> must equal the plain
     conversion bit for bit (checked against the reference's summation order is

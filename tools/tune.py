@@ -45,36 +45,76 @@ if "dot" in which:
     ab.tune("dot_ctas_per_sm", 0)
 
 if "gemv" in which:
+    # ACCBLAS_TUNE_GEMV="st:ar:unroll:variant:stages:intwords:taper[:pipe],..." restricts the sweep
+    import os
+    DT = {"f64": torch.float64, "f32": torch.float32, "f16": torch.float16}
+    spec = os.environ.get("ACCBLAS_TUNE_GEMV", "")
+    if spec:
+        cases = []
+        for item in spec.split(","):
+            st_s, ar_s, *rest = item.split(":")
+            cases.append((DT[st_s], DT[ar_s], *map(int, rest)))
+    else:
+        cases = [(st, ar, 2, v, 0, 3, 1)
+                 for st in (torch.float32, torch.float16, torch.float64)
+                 for ar in (torch.float64, torch.float32)
+                 for v in (4, 5, 2, 3, 4)]
     m = k = 16384
     for st in (torch.float32, torch.float16, torch.float64):
+        mine = [c for c in cases if c[0] == st]
+        if not mine:
+            continue
         A = torch.empty(m * k, dtype=st, device=dev)
         x = torch.empty(k, dtype=st, device=dev)
         y = torch.zeros(m, dtype=st, device=dev)
         h.fill_uniform(m, k, A, k, 42, 0)
         h.fill_uniform(k, 1, x, 1, 42, m * k)
-        for ar in (torch.float64, torch.float32):
-            for unroll, variant, stages, occ, taper in [(2, 4, 0, 3, 1), (2, 4, 0, 4, 1), (2, 4, 0, 3, 0),
-                                                         (2, 5, 0, 3, 1), (2, 2, 0, 3, 1), (2, 3, 0, 3, 1),
-                                                         (2, 4, 0, 3, 1), (2, 4, 0, 4, 1)]:
-                ab.tune("gemv_unroll", unroll)
-                ab.tune("gemv_variant", variant)
-                ab.tune("gemv_stages", stages)
-                ab.tune("gemv_occ", occ)
-                ab.tune("gemv_taper", taper)
-                ms = min_of_10(lambda: h.gemv(ar, m, k, 1.0, A, k, x, 1, 0.0, y, 1), torch)
-                gbs = gemv_bytes(m, k, A.element_size()) / ms / 1e6
-                key = (f"gemv Acc<{NAME[ar]},{NAME[st]}> unroll={unroll} variant={variant} "
-                       f"stages={stages} occ={occ} taper={taper}")
-                if key in results:
-                    key += " (repeat)"
-                results[key] = round(gbs, 1)
-                print(key, f"{gbs:8.1f} GB/s", flush=True)
+        for _, ar, unroll, variant, stages, occ, taper, *more in mine:
+            pipe = more[0] if more else -1
+            ab.tune("gemv_pipe", pipe)
+            ab.tune("gemv_unroll", unroll)
+            ab.tune("gemv_variant", variant)
+            ab.tune("gemv_stages", stages)
+            ab.tune("gemv_intwords", occ)
+            ab.tune("gemv_taper", taper)
+            ms = min_of_10(lambda: h.gemv(ar, m, k, 1.0, A, k, x, 1, 0.0, y, 1), torch)
+            gbs = gemv_bytes(m, k, A.element_size()) / ms / 1e6
+            key = (f"gemv Acc<{NAME[ar]},{NAME[st]}> unroll={unroll} variant={variant} "
+                   f"stages={stages} intwords={occ} taper={taper} pipe={pipe}")
+            while key in results:
+                key += " (repeat)"
+            results[key] = round(gbs, 1)
+            print(key, f"{gbs:8.1f} GB/s", flush=True)
         del A
     ab.tune("gemv_unroll", 2)
     ab.tune("gemv_variant", 0)
     ab.tune("gemv_stages", 0)
-    ab.tune("gemv_occ", 3)
+    ab.tune("gemv_intwords", 2)
     ab.tune("gemv_taper", 1)
+    ab.tune("gemv_pipe", -1)
+
+if "trsv" in which:
+    # min-of-10 time of every (uplo, diag) at n = 16384 on a well-conditioned
+    # triangle (scaled uniform entries, dominant diagonal)
+    n = 16384
+    for st in (torch.float32, torch.float64, torch.float16):
+        T = torch.empty(n * n, dtype=st, device=dev)
+        b = torch.empty(n, dtype=st, device=dev)
+        h.fill_uniform(n, n, T, n, 42, 0)
+        h.fill_uniform(n, 1, b, 1, 42, n * n)
+        T.mul_(0.01)
+        T.view(n, n).diagonal().fill_(1.0)
+        for ar in (torch.float64, torch.float32):
+            for uplo, diag in ((ab.LOWER, ab.UNIT), (ab.LOWER, ab.NON_UNIT),
+                               (ab.UPPER, ab.UNIT), (ab.UPPER, ab.NON_UNIT)):
+                xw = b.clone()
+                ms = min_of_10(lambda: h.trsv(ar, uplo, diag, n, T, n, xw, 1), torch)
+                key = (f"trsv Acc<{NAME[ar]},{NAME[st]}> "
+                       f"{'lower' if uplo == ab.LOWER else 'upper'}/"
+                       f"{'unit' if diag == ab.UNIT else 'nonunit'}")
+                results[key] = round(ms * 1e3, 1)
+                print(key, f"{ms * 1e3:8.1f} us", flush=True)
+        del T
 
 out = ROOT / "gpurun_out"
 out.mkdir(exist_ok=True)
