@@ -579,8 +579,10 @@ int accblas_tune(const char* key, int value)
         t.gemv_pipe = value;
     } else if (!strcmp(key, "gemv_intwords")) {
         t.gemv_intwords = value;
-    } else if (!strcmp(key, "trsv_variant")) {
-        t.trsv_variant = value;
+    } else if (!strcmp(key, "trsv_whole_block_spin")) {
+        t.trsv_whole_block_spin = value;
+    } else if (!strcmp(key, "trsv_l2_ahead")) {
+        t.trsv_l2_ahead = value;
     } else {
         accblas::set_error("unknown tuning key '%s'", key);
         return ACCBLAS_ERR_INVALID;

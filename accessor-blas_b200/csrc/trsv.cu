@@ -106,10 +106,71 @@ __device__ __forceinline__ void named_barrier_arrive(int id, int threads)
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// Four consecutive storage elements as RAW 32-bit words.  The words are only
+// taken apart by get<Ar>() in the conversion phase; pin() orders every use of
+// the words after the loads issued so far.  (With a typed struct the compiler
+// hoisted the half-word shuffles of fp16 storage to right behind each load and
+// reused ONE destination register for all eight loads of a panel: eight
+// serialised L2 round trips per block iteration -- ncu: 58 % of all stall
+// samples on those shuffles.)
 template <typename St>
 struct Quad {
-    St v[kEPL];
+    static constexpr int kWords = kEPL * static_cast<int>(sizeof(St)) / 4;
+    unsigned w[kWords];
+
+    __device__ __forceinline__ void pin()
+    {
+#pragma unroll
+        for (int i = 0; i < kWords; ++i) {
+            asm volatile("" : "+r"(w[i]));
+        }
+    }
+    __device__ __forceinline__ void set(int e, St value);
+    template <typename Ar>
+    __device__ __forceinline__ Ar get(int e) const;
 };
+
+template <>
+__device__ __forceinline__ void Quad<double>::set(int e, double value)
+{
+    w[2 * e] = static_cast<unsigned>(__double2loint(value));
+    w[2 * e + 1] = static_cast<unsigned>(__double2hiint(value));
+}
+template <>
+__device__ __forceinline__ void Quad<float>::set(int e, float value)
+{
+    w[e] = __float_as_uint(value);
+}
+template <>
+__device__ __forceinline__ void Quad<__half>::set(int e, __half value)
+{
+    const unsigned bits = __half_as_ushort(value);
+    const int word = e >> 1;
+    w[word] = (e & 1) ? ((w[word] & 0x0000ffffu) | (bits << 16))
+                      : ((w[word] & 0xffff0000u) | bits);
+}
+template <>
+template <typename Ar>
+__device__ __forceinline__ Ar Quad<double>::get(int e) const
+{
+    return to_ar<Ar, double>(__hiloint2double(static_cast<int>(w[2 * e + 1]),
+                                              static_cast<int>(w[2 * e])));
+}
+template <>
+template <typename Ar>
+__device__ __forceinline__ Ar Quad<float>::get(int e) const
+{
+    return to_ar<Ar, float>(__uint_as_float(w[e]));
+}
+template <>
+template <typename Ar>
+__device__ __forceinline__ Ar Quad<__half>::get(int e) const
+{
+    const unsigned short bits =
+        static_cast<unsigned short>((e & 1) ? (w[e >> 1] >> 16)
+                                            : (w[e >> 1] & 0xffffu));
+    return to_ar<Ar, __half>(__ushort_as_half(bits));
+}
 
 __device__ __forceinline__ uint2 ldg_stream_64(const void* p)
 {
@@ -140,18 +201,30 @@ __device__ __forceinline__ Quad<St> load_quad(const St* p, int valid)
         if (sizeof(St) == 8) {
             const uint4 a = ldg_stream_128(p);
             const uint4 b = ldg_stream_128(p + 2);
-            uint4* dst = reinterpret_cast<uint4*>(&q);
-            dst[0] = a;
-            dst[1] = b;
+            q.w[0] = a.x; q.w[1] = a.y; q.w[2] = a.z; q.w[3] = a.w;
+            q.w[4 % Quad<St>::kWords] = b.x;
+            q.w[5 % Quad<St>::kWords] = b.y;
+            q.w[6 % Quad<St>::kWords] = b.z;
+            q.w[7 % Quad<St>::kWords] = b.w;
         } else if (sizeof(St) == 4) {
-            *reinterpret_cast<uint4*>(&q) = ldg_stream_128(p);
+            const uint4 a = ldg_stream_128(p);
+            q.w[0] = a.x; q.w[1] = a.y;
+            q.w[2 % Quad<St>::kWords] = a.z;
+            q.w[3 % Quad<St>::kWords] = a.w;
         } else {
-            *reinterpret_cast<uint2*>(&q) = ldg_stream_64(p);
+            const uint2 a = ldg_stream_64(p);
+            q.w[0] = a.x; q.w[1] = a.y;
         }
     } else {
 #pragma unroll
+        for (int i = 0; i < Quad<St>::kWords; ++i) {
+            q.w[i] = 0u;
+        }
+#pragma unroll
         for (int e = 0; e < kEPL; ++e) {
-            q.v[e] = (e < valid) ? p[e] : zero_st<St>();
+            if (e < valid) {
+                q.set(e, p[e]);
+            }
         }
     }
     return q;
@@ -211,12 +284,18 @@ __device__ __forceinline__ void invert_subblock(Ar* T, Ar* inv_diag, int lane)
 // sum needs only TWO shuffle levels -- the shuffle unit handles one warp per
 // cycle per SM, so the previous "lane = column" layout (five levels for each
 // of 8 rows per warp) spent ~1300 cycles of every block step just shuffling.
-template <typename St, typename Ar, bool UPPER, bool UNIT, bool VECTOR>
+// TRACE = false (production): the timeline probes below compile away entirely
+// -- even predicated off they cost registers (this kernel sits at the 128
+// register limit of a 512-thread CTA) and scoreboard waits.
+template <typename St, typename Ar, bool UPPER, bool UNIT, bool VECTOR,
+          bool TRACE>
 __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     std::int64_t n, const St* __restrict__ A, std::int64_t lda,
     St* __restrict__ x, std::int64_t incx, Ar* xs,
-    unsigned* __restrict__ ticket, long long* __restrict__ trace)
+    unsigned* __restrict__ ticket, long long* __restrict__ trace_arg,
+    int l2_ahead, int whole_block_spin)
 {
+    long long* const trace = TRACE ? trace_arg : nullptr;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ar* D = reinterpret_cast<Ar*>(smem_raw);  // kB x kLD
     Ar* xcol = D + kB * kLD;                  // 2 x kB, staged x blocks
@@ -225,6 +304,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     Ar* inv_diag = xsol + kB;                 // kB
     Ar* scratch = inv_diag + kB;              // kB, rehearsal right-hand side
     __shared__ unsigned k_shared;
+    __shared__ int mode_s[2];
 
     const int tid = threadIdx.x;
     const int lane = tid & (kWarp - 1);
@@ -239,7 +319,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     const std::int64_t k = k_shared;  // position in the solve order
     // development aid: per-CTA phase timestamps (SM cycles / global ns)
 #define ACCBLAS_TRACE(slot, value)                  \
-    if (trace != nullptr && tid == 0) {             \
+    if (TRACE && trace != nullptr && tid == 0) {    \
         trace[k * 64 + (slot)] = (value);           \
     }
     ACCBLAS_TRACE(0, clock64());
@@ -275,7 +355,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                 const bool in_tri = UPPER ? (cc >= r) : (cc <= r);
                 Ar val;
                 if (r < bs && cc < bs && in_tri && !(UNIT && r == cc)) {
-                    val = to_ar<Ar, St>(q[it].v[e]);
+                    val = q[it].template get<Ar>(e);
                 } else {
                     val = (r == cc) ? Ar{1} : Ar{0};
                 }
@@ -294,6 +374,59 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
         invert_subblock<Ar, UPPER, UNIT>(D + (warp * kSB) * kLD + warp * kSB,
                                          inv_diag + warp * kSB, lane);
     }
+    __syncthreads();
+    // ---- M(g,t) = Inv_g * D(g,t) for every sub-block pair with t solved
+    //      before g, in place.  With these the solve of the diagonal tile is
+    //          x_g = Inv_g rhs_g - sum_{t<g} M(g,t) x_t
+    //      i.e. ONE 32x32 matrix-vector product between consecutive
+    //      sub-block solutions instead of two (update, then multiply by the
+    //      inverse).  192 k FMAs per CTA, done once, while the CTA would be
+    //      waiting for its predecessors anyway.
+    {
+        const int i = tid >> 4;         // row inside the 32 x 32 block
+        const int jp = (tid & 15) * 2;  // column pair
+        Ar out[6][2];
+        int slot = 0;
+#pragma unroll
+        for (int g = 1; g < kNSB; ++g) {
+#pragma unroll
+            for (int t = 0; t < g; ++t) {
+                const int mg = UPPER ? kNSB - 1 - g : g;  // memory sub-block
+                const int mt = UPPER ? kNSB - 1 - t : t;
+                const Ar* inv = D + (mg * kSB + i) * kLD + mg * kSB;
+                const Ar* blk = D + (mg * kSB) * kLD + mt * kSB + jp;
+                Ar o0 = Ar{}, o1 = Ar{};
+#pragma unroll 8
+                for (int kk = 0; kk < kSB; ++kk) {
+                    const Ar a = inv[kk];
+                    const Pair<Ar> d =
+                        *reinterpret_cast<const Pair<Ar>*>(blk + kk * kLD);
+                    o0 = fma_ar(a, d.a, o0);
+                    o1 = fma_ar(a, d.b, o1);
+                }
+                out[slot][0] = o0;
+                out[slot][1] = o1;
+                ++slot;
+            }
+        }
+        __syncthreads();
+        slot = 0;
+#pragma unroll
+        for (int g = 1; g < kNSB; ++g) {
+#pragma unroll
+            for (int t = 0; t < g; ++t) {
+                const int mg = UPPER ? kNSB - 1 - g : g;
+                const int mt = UPPER ? kNSB - 1 - t : t;
+                Pair<Ar> o;
+                o.a = out[slot][0];
+                o.b = out[slot][1];
+                *reinterpret_cast<Pair<Ar>*>(D + (mg * kSB + i) * kLD +
+                                             mt * kSB + jp) = o;
+                ++slot;
+            }
+        }
+    }
+    __syncthreads();
     ACCBLAS_TRACE(2, clock64());
 
     // Everything from here to the end of the diagonal solve runs TWICE:
@@ -311,18 +444,77 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
         r = (r < n) ? r : n - 1;  // padded rows re-read a valid row
         row_ptr = A + r * lda + kEPL * seg;
     }
+    // panels of a 128-column block are walked in the order their x entries
+    // are produced (ascending columns for lower, descending for upper)
     auto load_panel = [&](std::int64_t jj, int p, Quad<St> (&dst)[Q]) {
         const std::int64_t pbj = UPPER ? nb - 1 - jj : jj;
-        const std::int64_t c0 = pbj * kB + p * (16 * Q);
+        const int pm = UPPER ? NP - 1 - p : p;  // memory panel
+        const std::int64_t c0 = pbj * kB + pm * (16 * Q);
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
             const std::int64_t col = c0 + 16 * i + kEPL * seg;
             const std::int64_t left = n - col;
             const int valid =
                 left >= kEPL ? kEPL : (left > 0 ? static_cast<int>(left) : 0);
-            dst[i] = load_quad<St, VECTOR>(row_ptr + c0 + 16 * i, valid);
+            if (l2_ahead == -1) {
+                // experiment: no memory traffic at all (results are wrong)
+#pragma unroll
+                for (int w = 0; w < Quad<St>::kWords; ++w) {
+                    dst[i].w[w] = 0u;
+                }
+            } else {
+                dst[i] = load_quad<St, VECTOR>(row_ptr + c0 + 16 * i, valid);
+            }
         }
     };
+    // warp 0: copy the 128 progress-vector entries of physical block `pblock`
+    // into x buffer `b` (L2 -> shared memory, 16 bytes per copy)
+    auto prefetch_x = [&](std::int64_t pblock, int b) {
+        constexpr int kChunks = kB * static_cast<int>(sizeof(Ar)) / 16;
+        const char* src = reinterpret_cast<const char*>(xs + pblock * kB);
+        const unsigned dst = static_cast<unsigned>(
+            __cvta_generic_to_shared(xcol + b * kB));
+#pragma unroll
+        for (int c = lane; c < kChunks; c += kWarp) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                             dst + c * 16),
+                         "l"(src + c * 16)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // Ask L2 for the off-diagonal tiles of a GROUP of consecutive blocks of
+    // the solve order, one group ahead.  Two reasons:
+    //  * the register pipeline above keeps only ONE panel in flight per CTA,
+    //    so a block iteration would be bounded by the DRAM latency; with the
+    //    lines already in L2 the same loads return in a few hundred cycles;
+    //  * a 128-column tile is only 256 / 512 / 1024 bytes per row (fp16 / fp32
+    //    / fp64) at a row stride of tens of KB -- poor DRAM page locality.  A
+    //    group is l2_group_bytes (>= 1 KB) of CONSECUTIVE bytes per row.
+    // Thread = lines seg, seg + 4, ... of its own row.
+    const int group_blocks =
+        l2_ahead > 0 ? max(1, l2_ahead / (kB * static_cast<int>(sizeof(St))))
+                     : 0;
+    auto l2_prefetch_group = [&](std::int64_t j0) {
+        // blocks j0 .. j0 + group_blocks - 1 of the solve order (dependencies
+        // only: jj < k), as one contiguous column range
+        std::int64_t j1 = j0 + group_blocks;
+        j1 = j1 < k ? j1 : k;
+        if (j0 >= j1) {
+            return;
+        }
+        const std::int64_t c_lo = (UPPER ? nb - j1 : j0) * kB;
+        std::int64_t c_hi = (UPPER ? nb - j0 : j1) * kB;
+        c_hi = c_hi < n ? c_hi : n;
+        constexpr int kLineElems = 128 / static_cast<int>(sizeof(St));
+        const St* row_base = row_ptr - kEPL * seg;
+        for (std::int64_t c = c_lo + seg * kLineElems; c < c_hi;
+             c += 4 * kLineElems) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(row_base + c));
+        }
+    };
+    const int mem_sub = trow >> 5;
+    const int grp = UPPER ? kNSB - 1 - mem_sub : mem_sub;  // solve index
 
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
@@ -339,15 +531,83 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
         const std::int64_t deps = real ? k : 0;
 
         // ---- off-diagonal blocks, in solve order; the loads of the next
-        //      panel are in flight while the current one is consumed
+        //      panel are in flight while the current one is consumed.
+        //      The x block a panel needs is fetched one block AHEAD with
+        //      cp.async (L2 -> shared memory, no registers): a CTA that is
+        //      behind the chain finds its x already in shared memory and pays
+        //      no L2 round trip per block ("fast": one barrier, 128 columns of
+        //      FMAs).  A CTA that has caught up finds sentinels; it then polls
+        //      the block 32 entries at a time, in the order the producing CTA
+        //      publishes its sub-block solutions, so that only the last 32
+        //      columns' FMAs follow the arrival of the block's last sub-block.
         Quad<St> cur[Q];
         if (deps > 0) {
             load_panel(0, 0, cur);
+            if (warp == 0) {
+                prefetch_x(UPPER ? nb - 1 : 0, 0);
+            }
+            if (group_blocks > 0) {
+                // the rest of group 0 (block 0 itself is being loaded)
+                l2_prefetch_group(0);
+            }
         }
         int buf = 0;
+        const bool phase_log =
+            TRACE && trace != nullptr && tid == 0 && k == nb - 1;
+        long long ph[5] = {0, 0, 0, 0, 0};
+        long long ph_t = 0;
         for (std::int64_t jj = 0; jj < deps; ++jj) {
+            const std::int64_t pbj = UPPER ? nb - 1 - jj : jj;
+            if (phase_log) {
+                ph_t = clock64();
+            }
+            Ar* xblk = xcol + buf * kB;
+            bool fast = false;
+            if (group_blocks > 0 && jj % group_blocks == 0) {
+                l2_prefetch_group(jj + group_blocks);
+            }
+            // warp 0: is the prefetched copy of this x block complete?  If not,
+            // ask L2 once more for the missing entries -- all of them in one
+            // go, and the answers are looked at only after the panel has been
+            // widened, so the round trip is hidden
+            Ar repoll[kNSB];
+            bool ok = true;
+            if (warp == 0) {
+                if (jj == deps - 1) {
+                    ACCBLAS_TRACE(3, clock64());
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();  // lanes read entries other lanes copied
+#pragma unroll
+                for (int sb = 0; sb < kNSB; ++sb) {
+                    const int idx = sb * kSB + lane;
+                    repoll[sb] = Ar{0};
+                    if (pbj * kB + idx < n) {
+                        repoll[sb] = xblk[idx];
+                        ok = ok && !Sentinel<Ar>::is(repoll[sb]);
+                    } else {
+                        xblk[idx] = Ar{0};
+                    }
+                }
+                ok = __all_sync(0xffffffffu, ok);
+                if (!ok) {
+#pragma unroll
+                    for (int sb = 0; sb < kNSB; ++sb) {
+                        const std::int64_t pc = pbj * kB + sb * kSB + lane;
+                        if (pc < n && Sentinel<Ar>::is(repoll[sb])) {
+                            repoll[sb] = ld_volatile(xs + pc);
+                        }
+                    }
+                }
+            }
+            if (phase_log) {
+                const long long now = clock64();
+                ph[0] += now - ph_t;  // x prefetch wait + check (+ re-poll issue)
+                ph_t = now;
+            }
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
+                const int pm = UPPER ? NP - 1 - p : p;
                 Quad<St> nxt[Q];
                 if (p + 1 < NP) {
                     load_panel(jj, p + 1, nxt);
@@ -363,80 +623,140 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                 for (int i = 0; i < Q; ++i) {
 #pragma unroll
                     for (int e = 0; e < kEPL; ++e) {
-                        cv[i][e] = to_ar<Ar, St>(cur[i].v[e]);
+                        cv[i][e] = cur[i].template get<Ar>(e);
                         pin_register(cv[i][e]);
                     }
                 }
-                if (p == 0) {
-                    if (jj == deps - 1) {
-                        ACCBLAS_TRACE(3, clock64());
+                if (p == 0 && phase_log) {
+                    const long long now = clock64();
+                    ph[1] += now - ph_t;  // next-panel loads issued, panel widened
+                    ph_t = now;
+                }
+                if (p == 0 && warp == 0) {
+                    if (!ok) {
+                        ok = true;
+#pragma unroll
+                        for (int sb = 0; sb < kNSB; ++sb) {
+                            const int idx = sb * kSB + lane;
+                            if (pbj * kB + idx < n) {
+                                xblk[idx] = repoll[sb];
+                                ok = ok && !Sentinel<Ar>::is(repoll[sb]);
+                            }
+                        }
+                        ok = __all_sync(0xffffffffu, ok);
                     }
-                    if (warp == 0) {
-                        const std::int64_t pbj = UPPER ? nb - 1 - jj : jj;
-                        const std::int64_t pc = pbj * kB + lane * kEPL;
-                        const std::int64_t left = n - pc;
-                        const int valid =
-                            left >= kEPL
-                                ? kEPL
-                                : (left > 0 ? static_cast<int>(left) : 0);
-                        Ar v[kEPL];
-                        bool ok;
+                    if (!ok && whole_block_spin) {
+                        // caught up with the chain: spin on whatever is still
+                        // missing, all of it in flight at once
                         do {
                             ok = true;
 #pragma unroll
-                            for (int e = 0; e < kEPL; ++e) {
-                                if (e < valid) {
-                                    v[e] = ld_volatile(xs + pc + e);
-                                    ok = ok && !Sentinel<Ar>::is(v[e]);
-                                } else {
-                                    v[e] = Ar{0};
+                            for (int sb = 0; sb < kNSB; ++sb) {
+                                const std::int64_t pc =
+                                    pbj * kB + sb * kSB + lane;
+                                if (pc < n && Sentinel<Ar>::is(repoll[sb])) {
+                                    repoll[sb] = ld_volatile(xs + pc);
                                 }
                             }
-                        } while (!__all_sync(0xffffffffu, ok));
 #pragma unroll
-                        for (int e = 0; e < kEPL; ++e) {
-                            xcol[buf * kB + lane * kEPL + e] = v[e];
+                            for (int sb = 0; sb < kNSB; ++sb) {
+                                const int idx = sb * kSB + lane;
+                                if (pbj * kB + idx < n) {
+                                    xblk[idx] = repoll[sb];
+                                    ok = ok && !Sentinel<Ar>::is(repoll[sb]);
+                                }
+                            }
+                            ok = __all_sync(0xffffffffu, ok);
+                        } while (!ok);
+                    }
+                    fast = ok;
+                    if (lane == 0) {
+                        mode_s[buf] = fast ? 1 : 0;
+                    }
+                }
+                constexpr int SUBS = kNSB / NP;  // sub-blocks per panel
+#pragma unroll
+                for (int t = 0; t < SUBS; ++t) {
+                    // t-th sub-block of this panel to arrive; ts = its
+                    // position inside the panel in memory order
+                    const int ts = UPPER ? SUBS - 1 - t : t;
+                    const int sbm = pm * SUBS + ts;  // memory sub-block
+                    const bool first = p == 0 && t == 0;
+                    if (first || !fast) {
+                        if (warp == 0 && !fast) {
+                            const int idx = sbm * kSB + lane;
+                            const std::int64_t pc = pbj * kB + idx;
+                            if (pc < n) {
+                                Ar v = xblk[idx];
+                                while (Sentinel<Ar>::is(v)) {
+                                    v = ld_volatile(xs + pc);
+                                }
+                                xblk[idx] = v;
+                            }
                         }
-                        if (jj == deps - 1) {
+                        if (warp == 0 && jj == deps - 1 &&
+                            (fast || (p == NP - 1 && t == SUBS - 1))) {
                             ACCBLAS_TRACE(4, clock64());
                             ACCBLAS_TRACE(13, static_cast<long long>(
                                                   globaltimer_ns()));
                         }
+                        __syncthreads();
+                        if (first && phase_log) {
+                            const long long now = clock64();
+                            ph[2] += now - ph_t;  // re-poll evaluation + first barrier
+                            ph_t = now;
+                        }
+                        if (first) {
+                            fast = mode_s[buf] != 0;
+                            // every warp is past block jj - 1: its x buffer
+                            // can take block jj + 1
+                            if (warp == 0 && jj + 1 < deps) {
+                                prefetch_x(UPPER ? nb - 2 - jj : jj + 1, buf ^ 1);
+                            }
+                        }
                     }
-                    __syncthreads();
-                    if (jj == deps - 1) {
-                        ACCBLAS_TRACE(5, clock64());
-                    }
-                }
-                const Ar* xb = xcol + buf * kB + p * (16 * Q) + kEPL * seg;
-                const bool tile_probe =
-                    trace != nullptr && tid == 0 && jj == deps - 1 && p == NP - 1;
-                if (tile_probe) {
-                    Ar first = xb[0];
-                    pin_register(first);
-                    trace[k * 64 + 32] = clock64();
-                }
+                    const Ar* xb = xblk + pm * (16 * Q) + kEPL * seg;
 #pragma unroll
-                for (int i = 0; i < Q; ++i) {
+                    for (int ii = 0; ii < 2; ++ii) {
+                        const int i = 2 * ts + ii;
 #pragma unroll
-                    for (int e = 0; e < kEPL; ++e) {
-                        const int slot = (p * Q + i) % NACC;
-                        acc[slot] = fma_ar(cv[i][e], xb[16 * i + e], acc[slot]);
+                        for (int e = 0; e < kEPL; ++e) {
+                            const int slot = (p * Q + i) % NACC;
+                            acc[slot] =
+                                fma_ar(cv[i][e], xb[16 * i + e], acc[slot]);
+                        }
                     }
-                }
-                if (tile_probe) {
-#pragma unroll
-                    for (int i = 0; i < NACC; ++i) {
-                        pin_register(acc[i]);
-                    }
-                    trace[k * 64 + 33] = clock64();
                 }
 #pragma unroll
                 for (int i = 0; i < Q; ++i) {
+                    // nothing touches the words of the next panel before this
+                    // point: its loads stay in flight across the iteration
+                    nxt[i].pin();
                     cur[i] = nxt[i];
                 }
             }
+            if (phase_log) {
+#pragma unroll
+                for (int i = 0; i < NACC; ++i) {
+                    pin_register(acc[i]);
+                }
+                const long long now = clock64();
+                ph[3] += now - ph_t;  // FMAs (and later barriers on the slow path)
+                ph_t = now;
+            }
+            if (phase_log && fast) {
+                ++ph[4];
+            }
             buf ^= 1;
+        }
+        if (real) {
+            ACCBLAS_TRACE(5, clock64());
+            if (phase_log) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    trace[k * 64 + 48 + i] = ph[i];
+                }
+            }
         }
         {
 #pragma unroll
@@ -452,45 +772,32 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
             if (seg == 0 && r0 + trow < n) {  // padded rows stay zero
                 rhs_cur[trow] -= v;
             }
-            if (real && trace != nullptr && tid == 0) {
-                pin_register(v);
-                trace[k * 64 + 34] = clock64();
-            }
         }
-        __syncthreads();
+        // "rhs of my sub-block is complete": its 32 rows belong to the four
+        // warps of this group only
+        named_barrier_sync(1 + grp, 4 * kWarp);
         if (real) {
             ACCBLAS_TRACE(6, clock64());
         }
 
-        // ---- diagonal block: the four 32-wide sub-blocks in solve order.
-        //      Warp group g (4 warps = the 128 threads whose rows lie in the
-        //      g-th sub-block to be solved) multiplies by that sub-block's
-        //      inverse and publishes; every later group then subtracts the new
-        //      entries from its own rows.  Synchronisation is by NAMED barriers
-        //      between exactly the warps involved (the solving group only
-        //      arrives and moves on), not by CTA-wide barriers:
-        //        id 1+g : "x of group g is in shared memory"  (group g arrives,
-        //                 later groups wait)          128 * (4 - g) threads
-        //        id 4+g : "rhs of group g is complete" (within group g)  128
-        const int mem_sub = trow >> 5;
-        const int grp = UPPER ? kNSB - 1 - mem_sub : mem_sub;
-        const bool probe = real && trace != nullptr && seg == 0;
-#pragma unroll 1
-        for (int step = 0; step < kNSB; ++step) {
-            const int s = UPPER ? kNSB - 1 - step : step;  // memory order
-            // a thread owns the column pairs 32 s + 2 seg + 8 e + {0, 1}
-            const int c2 = s * kSB + 2 * seg;
-            if (grp == step) {
-                if (step > 0) {
-                    named_barrier_sync(4 + step, 4 * kWarp);
-                }
-                if (probe && (trow & 31) == 0) {
-                    trace[k * 64 + 16 + 4 * step] = clock64();
-                }
+        // ---- diagonal block.  Warp group g = the 128 threads whose rows lie
+        //      in the g-th sub-block to be solved.
+        //        y_g = Inv_g rhs_g                  all groups at once
+        //        x_g = y_g - sum_{t<g} M(g,t) x_t   chain, one product per link
+        //      Synchronisation by NAMED barriers between exactly the warps
+        //      involved; the solving group only arrives and moves on:
+        //        id 1+g : "rhs of group g is complete"      128 threads
+        //        id 5+s : "x_s is in shared memory"         128 * (4 - s)
+        {
+            const bool probe = TRACE && real && trace != nullptr && seg == 0 &&
+                               (trow & 31) == 0;
+            const int c_own = mem_sub * kSB + 2 * seg;
+            Ar y;
+            {
                 const Pair<Ar>* Trow =
-                    reinterpret_cast<const Pair<Ar>*>(D + trow * kLD + c2);
+                    reinterpret_cast<const Pair<Ar>*>(D + trow * kLD + c_own);
                 const Pair<Ar>* v =
-                    reinterpret_cast<const Pair<Ar>*>(rhs_cur + c2);
+                    reinterpret_cast<const Pair<Ar>*>(rhs_cur + c_own);
                 Ar p0 = Ar{}, p1 = Ar{};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -499,55 +806,81 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                     p0 = fma_ar(t.a, w.a, p0);
                     p1 = fma_ar(t.b, w.b, p1);
                 }
-                Ar sol = p0 + p1;
-                sol += __shfl_xor_sync(0xffffffffu, sol, 1);
-                sol += __shfl_xor_sync(0xffffffffu, sol, 2);
-                if (seg == 0) {
-                    // round through storage: later rows see what the
-                    // accessor re-reads
-                    const St stored = to_st<St, Ar>(sol);
-                    const Ar back = to_ar<Ar, St>(stored);
-                    xsol[trow] = back;
-                    if (probe && (trow & 31) == 0) {
-                        trace[k * 64 + 17 + 4 * step] = clock64();
-                    }
+                y = p0 + p1;
+                if (probe && grp == 0) {
+                    pin_register(y);
+                    trace[k * 64 + 35] = clock64();
                 }
-                if (step + 1 < kNSB) {
-                    named_barrier_arrive(1 + step, 4 * kWarp * (kNSB - step));
+                y += __shfl_xor_sync(0xffffffffu, y, 1);
+                y += __shfl_xor_sync(0xffffffffu, y, 2);
+                if (probe && grp == 0) {
+                    pin_register(y);
+                    trace[k * 64 + 36] = clock64();
                 }
-                if (real && seg == 0) {
-                    // publish: progress vector first (the next block row spins
-                    // on it), then the caller's x.  No barrier follows in this
-                    // warp group, so the stores cost nothing here.
-                    const std::int64_t gi = r0 + trow;
-                    if (gi < n) {
-                        const Ar val = xsol[trow];
-                        st_volatile(xs + gi, Sentinel<Ar>::clean(val));
-                        x[gi * incx] = to_st<St, Ar>(val);
-                    }
-                }
-            } else if (grp > step) {
-                named_barrier_sync(1 + step, 4 * kWarp * (kNSB - step));
-                const Pair<Ar>* Drow =
-                    reinterpret_cast<const Pair<Ar>*>(D + trow * kLD + c2);
-                const Pair<Ar>* xv =
-                    reinterpret_cast<const Pair<Ar>*>(xsol + c2);
-                Ar p0 = Ar{}, p1 = Ar{};
+            }
+            Ar corr = Ar{};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const Pair<Ar> t = Drow[4 * e];
-                    const Pair<Ar> w = xv[4 * e];
-                    p0 = fma_ar(t.a, w.a, p0);
-                    p1 = fma_ar(t.b, w.b, p1);
-                }
-                Ar sum = p0 + p1;
-                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                if (seg == 0) {
-                    rhs_cur[trow] -= sum;
-                }
-                if (probe && grp == step + 1 && (trow & 31) == 0) {
-                    trace[k * 64 + 18 + 4 * step] = clock64();
+            for (int step = 0; step < kNSB; ++step) {
+                const int ms = UPPER ? kNSB - 1 - step : step;  // memory order
+                if (grp == step) {
+                    if (probe) {
+                        trace[k * 64 + 16 + 4 * step] = clock64();
+                    }
+                    // round through storage: later rows see what the accessor
+                    // re-reads
+                    const St stored = to_st<St, Ar>(y - corr);
+                    const Ar back = to_ar<Ar, St>(stored);
+                    if (seg == 0) {
+                        xsol[trow] = back;
+                    }
+                    if (step + 1 < kNSB) {
+                        // (PTX ISA, bar.arrive example: a store to shared
+                        // memory followed by bar.arrive is visible to the
+                        // threads that bar.sync on the same barrier)
+                        named_barrier_arrive(5 + step,
+                                             4 * kWarp * (kNSB - step));
+                    }
+                    if (probe) {
+                        trace[k * 64 + 17 + 4 * step] = clock64();
+                        trace[k * 64 + 40 + step] =
+                            static_cast<long long>(globaltimer_ns());
+                    }
+                    if (real && seg == 0) {
+                        // publish: progress vector first (the next block row
+                        // spins on it), then the caller's x
+                        const std::int64_t gi = r0 + trow;
+                        if (gi < n) {
+                            st_volatile(xs + gi, Sentinel<Ar>::clean(back));
+                            x[gi * incx] = stored;
+                        }
+                    }
+                } else if (grp > step) {
+                    // M(g, step) entries of my row: constants, fetched before
+                    // the wait
+                    const int c2 = ms * kSB + 2 * seg;
+                    const Pair<Ar>* Mrow =
+                        reinterpret_cast<const Pair<Ar>*>(D + trow * kLD + c2);
+                    Pair<Ar> mreg[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        mreg[e] = Mrow[4 * e];
+                        pin_register(mreg[e].a);
+                        pin_register(mreg[e].b);
+                    }
+                    named_barrier_sync(5 + step, 4 * kWarp * (kNSB - step));
+                    const Pair<Ar>* xv =
+                        reinterpret_cast<const Pair<Ar>*>(xsol + c2);
+                    Ar p0 = Ar{}, p1 = Ar{};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const Pair<Ar> w = xv[4 * e];
+                        p0 = fma_ar(mreg[e].a, w.a, p0);
+                        p1 = fma_ar(mreg[e].b, w.b, p1);
+                    }
+                    Ar sum = p0 + p1;
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    corr += sum;
                 }
             }
         }
@@ -574,12 +907,13 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     }
 }
 
-template <typename St, typename Ar, bool UPPER, bool UNIT, bool VECTOR>
+template <typename St, typename Ar, bool UPPER, bool UNIT, bool VECTOR,
+          bool TRACE = false>
 int launch_one(std::int64_t n, const St* A, std::int64_t lda, St* x,
                std::int64_t incx, Ar* xs, unsigned* ticket, long long* trace,
                cudaStream_t stream)
 {
-    auto kernel = trsv_kernel<St, Ar, UPPER, UNIT, VECTOR>;
+    auto kernel = trsv_kernel<St, Ar, UPPER, UNIT, VECTOR, TRACE>;
     const size_t smem = sizeof(Ar) * (kB * kLD + 6 * kB);
     // the opt-in is per device (and per instantiation)
     static bool configured[64] = {};
@@ -595,7 +929,8 @@ int launch_one(std::int64_t n, const St* A, std::int64_t lda, St* x,
     }
     const std::int64_t nb = (n + kB - 1) / kB;
     kernel<<<static_cast<unsigned>(nb), kThreads, smem, stream>>>(
-        n, A, lda, x, incx, xs, ticket, trace);
+        n, A, lda, x, incx, xs, ticket, trace, tuning().trsv_l2_ahead,
+        tuning().trsv_whole_block_spin);
     ACCBLAS_CUDA(cudaGetLastError());
     return ACCBLAS_OK;
 }
@@ -611,7 +946,9 @@ int launch_trsv(Handle* h, int uplo, int diag, std::int64_t n, const void* A_v,
     const St* A = static_cast<const St*>(A_v);
     St* x = static_cast<St*>(x_v);
     // progress vector: n arithmetic values, all sentinel between calls
-    const size_t need = static_cast<size_t>(n) * sizeof(Ar);
+    // whole 128-entry blocks: the kernel prefetches x a block at a time
+    const size_t need =
+        static_cast<size_t>((n + kB - 1) / kB) * kB * sizeof(Ar);
     void* old_ws = h->ws;
     int rc = ensure_workspace(h, kScratchBytes + need, stream);
     if (rc != ACCBLAS_OK) {
@@ -635,6 +972,15 @@ int launch_trsv(Handle* h, int uplo, int diag, std::int64_t n, const void* A_v,
         (static_cast<std::uint64_t>(lda) * sizeof(St)) % 16 == 0;
     const bool upper = uplo == ACCBLAS_UPPER;
     const bool unit = diag == ACCBLAS_UNIT;
+    if (trace != nullptr) {
+        // development timeline (tools/trsv_trace.py): one instantiation only
+        if (upper || !unit || !vec) {
+            set_error("trsv trace: lower / unit / aligned operands only");
+            return ACCBLAS_ERR_UNSUPPORTED;
+        }
+        return launch_one<St, Ar, false, true, true, true>(
+            n, A, lda, x, incx, xs, ticket, trace, stream);
+    }
 #define ACCBLAS_TRSV_CASE(U, N, V)                                          \
     if (upper == U && unit == N && vec == V) {                              \
         return launch_one<St, Ar, U, N, V>(n, A, lda, x, incx, xs, ticket,  \

@@ -15,7 +15,8 @@ struct Tuning {
     int gemv_intwords = 2;     // Acc<fp64,fp16>: words per 128-bit vector widened on the integer pipes (rest: F2F)
     int gemv_taper = 1;        // shorter row groups at the end of the grid
     int gemv_stages = 0;       // 0 = register path, 2..4 = bulk-copy ring depth
-    int trsv_variant = 0;      // 0 = default
+    int trsv_whole_block_spin = 1;  // TRSV: a caught-up CTA waits for a whole x block (1) or 32 entries at a time (0)
+    int trsv_l2_ahead = 1024;  // TRSV: bytes per row of the groups of off-diagonal tiles requested into L2 one group ahead (0 = off)
 };
 
 Tuning& tuning();

@@ -293,6 +293,38 @@ def test_trsv_parity(oracle, ab, handle, ar, st, n, upper, unit, transpose):
         assert err <= TRSV_TOL[(ar, st)] * max(1.0, n / 300), (err, ref_err)
 
 
+@pytest.mark.parametrize("whole,group", [(1, 1024), (0, 1024), (1, 0), (0, 0), (1, 4096)])
+def test_trsv_wait_modes_give_identical_results(oracle, ab, handle, whole, group):
+    """How a caught-up CTA waits for x (whole block / 32 entries at a time) and
+    whether tiles are requested into L2 ahead of time must not change a bit of
+    the result (many block rows: the chain, the x prefetch and both wait modes
+    are all exercised)."""
+    n, lda = 3000, 3008
+    LU = lu_fixture(n, seed=31, lda=lda)
+    try:
+        for ar, st, upper, unit in ((torch.float64, torch.float32, False, True),
+                                    (torch.float32, torch.float16, False, True),
+                                    (torch.float64, torch.float64, True, False)):
+            A = oracle.convert(LU, NP[st])
+            b = stored(oracle, n, st, seed=13)
+            outs = []
+            for w, g in ((1, 1024), (whole, group)):
+                ab.tune("trsv_whole_block_spin", w)
+                ab.tune("trsv_l2_ahead", g)
+                xd = dev(b)
+                handle.trsv(ar, ab.UPPER if upper else ab.LOWER, ab.UNIT if unit else ab.NON_UNIT,
+                            n, dev(A), lda, xd, 1)
+                torch.cuda.synchronize()
+                outs.append(host(xd))
+            assert np.array_equal(outs[0], outs[1], equal_nan=True), (ar, st, whole, group)
+            if unit:
+                exact = oracle.exact_trsv(A, n, lda, b, upper, unit)
+                assert oracle.l1_rel_error(exact, outs[0]) <= TRSV_TOL[(ar, st)] * n / 300
+    finally:
+        ab.tune("trsv_whole_block_spin", 1)
+        ab.tune("trsv_l2_ahead", 1024)
+
+
 def test_trsv_repeated_calls_and_strided_x(oracle, ab, handle):
     n, lda, incx = 700, 704, 2
     LU = lu_fixture(n, seed=5, lda=lda)

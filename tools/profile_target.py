@@ -53,12 +53,17 @@ if "trsv" in which:
     h.fill_uniform(n, n, g, n, 42, 0)
     LU, _ = torch.linalg.lu_factor(g.view(n, n))
     del g
-    A = LU.contiguous().view(-1).to(f32)
+    import os
+    pairs = os.environ.get("ACCBLAS_PROFILE_TRSV", "f64:f32").split(",")
+    DT = {"f64": f64, "f32": f32, "f16": f16}
+    for pair in pairs:
+        ar_s, st_s = pair.split(":")
+        A = LU.contiguous().view(-1).to(DT[st_s])
+        b = torch.empty(n, dtype=DT[st_s], device=dev)
+        h.fill_uniform(n, 1, b, 1, 42, n * n)
+        for _ in range(2):
+            x = b.clone()
+            h.trsv(DT[ar_s], ab.LOWER, ab.UNIT, n, A, n, x, 1)
+        torch.cuda.synchronize()
     del LU
-    b = torch.empty(n, dtype=f32, device=dev)
-    h.fill_uniform(n, 1, b, 1, 42, n * n)
-    for _ in range(2):
-        x = b.clone()
-        h.trsv(f64, ab.LOWER, ab.UNIT, n, A, n, x, 1)
-    torch.cuda.synchronize()
 print("profile target done")

@@ -104,14 +104,16 @@ if "trsv" in which:
         h.fill_uniform(n, 1, b, 1, 42, n * n)
         T.mul_(0.01)
         T.view(n, n).diagonal().fill_(1.0)
-        for ar in (torch.float64, torch.float32):
-            for uplo, diag in ((ab.LOWER, ab.UNIT), (ab.LOWER, ab.NON_UNIT),
-                               (ab.UPPER, ab.UNIT), (ab.UPPER, ab.NON_UNIT)):
+        import os
+        aheads = [int(v) for v in os.environ.get("ACCBLAS_TUNE_TRSV_AHEAD", "3").split(",")]
+        for ar, ahead in itertools.product((torch.float64, torch.float32), aheads):
+            ab.tune("trsv_l2_ahead", ahead)
+            for uplo, diag in ((ab.LOWER, ab.UNIT), (ab.UPPER, ab.NON_UNIT)):
                 xw = b.clone()
                 ms = min_of_10(lambda: h.trsv(ar, uplo, diag, n, T, n, xw, 1), torch)
                 key = (f"trsv Acc<{NAME[ar]},{NAME[st]}> "
                        f"{'lower' if uplo == ab.LOWER else 'upper'}/"
-                       f"{'unit' if diag == ab.UNIT else 'nonunit'}")
+                       f"{'unit' if diag == ab.UNIT else 'nonunit'} l2_ahead={ahead}")
                 results[key] = round(ms * 1e3, 1)
                 print(key, f"{ms * 1e3:8.1f} us", flush=True)
         del T
