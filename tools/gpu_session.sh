@@ -12,4 +12,4 @@ timeout 900 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.log 2> gpur
 echo "bench exit $?" >> gpurun_out/status.txt
 "$@"
 cat gpurun_out/status.txt
-tail -5 gpurun_out/t_main.log gpurun_out/t_trsv.log gpurun_out/smoke.log
+for f in gpurun_out/t_main.log gpurun_out/t_trsv.log gpurun_out/smoke.log; do tail -n 5 "$f"; done
