@@ -12,18 +12,25 @@
 //   * off-diagonal updates done GEMV-style with 4 lanes per row (16
 //     consecutive elements per load instruction and row, full sectors): the
 //     next panel's L1-bypassing loads are in flight while the current one is
-//     consumed, the panel is widened to the arithmetic type BEFORE the wait
-//     for the matching x block, and a row sum needs two shuffle levels;
+//     consumed (raw-word registers nothing touches before the conversion
+//     phase), the panel is widened to the arithmetic type BEFORE the matching
+//     x block is looked at, and a row sum needs two shuffle levels; tiles of
+//     later blocks are requested into L2 ahead of time;
 //   * progress communicated through the solution itself: solved entries are
 //     published (already rounded through the storage type, as the reference's
 //     accessor write/read does) into a workspace vector that starts out as a
-//     NaN sentinel; consumers poll the values they need with volatile loads, so
-//     one L2 round trip carries both "ready" and the data -- no flag, no
-//     fence, no acquire/release pair on the critical path;
+//     NaN sentinel -- no flag, no fence, no acquire/release pair.  Consumers
+//     fetch the next x block one block ahead with cp.async (L2 -> shared
+//     memory); a CTA that is behind the chain never waits for L2, a CTA that
+//     has caught up re-polls the missing entries, all of them in flight at
+//     once;
 //   * the diagonal 128x128 tile lives in shared memory (leading dimension 136
 //     so 16-byte loads are conflict-free); each of its four 32x32 diagonal
 //     sub-blocks is inverted by one warp, lane j = column j by substitution in
-//     registers, and the solve walks the sub-blocks left-looking;
+//     registers; then M(g,t) = Inv_g D(g,t) is formed in place, so that the
+//     solve x_g = Inv_g rhs_g - sum_{t<g} M(g,t) x_t has ONE 32x32 product
+//     between consecutive sub-block solutions; warp groups hand the sub-block
+//     solutions to each other through named barriers;
 //   * the reduction + diagonal-solve code is rehearsed once on scratch data
 //     while the CTA waits, so it is warm in the instruction cache when it
 //     runs for real on the critical path.
