@@ -126,6 +126,38 @@ class Handle:
             dtype_code(result.dtype), n, _dev_ptr(x), incx, _dev_ptr(y), incy,
             _dev_ptr(result), _stream_ptr(stream)))
 
+    # ---- multi-GPU DOT with the all-reduce inside the kernel (peer memory)
+    def peer_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this GPU's mailbox."""
+        import ctypes
+        buf = ctypes.create_string_buffer(64)
+        capi.check(self._lib.accblas_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_connect_ipc(self, world: int, rank: int, handles: bytes) -> None:
+        assert len(handles) == 64 * world
+        capi.check(self._lib.accblas_peer_connect_ipc(self._h, world, rank, handles))
+
+    def peer_mailbox(self) -> int:
+        import ctypes
+        ptr = ctypes.c_void_p()
+        capi.check(self._lib.accblas_peer_mailbox(self._h, ctypes.byref(ptr)))
+        return ptr.value
+
+    def peer_connect_ptrs(self, world: int, rank: int, mailboxes, devices) -> None:
+        import ctypes
+        ptrs = (ctypes.c_void_p * world)(*mailboxes)
+        devs = (ctypes.c_int * world)(*devices)
+        capi.check(self._lib.accblas_peer_connect_ptrs(self._h, world, rank, ptrs, devs))
+
+    def dot_allreduce(self, ar, n: int, x: torch.Tensor, incx: int, y: torch.Tensor,
+                      incy: int, result: torch.Tensor, stream=None) -> None:
+        assert x.dtype == y.dtype
+        capi.check(self._lib.accblas_dot_allreduce(
+            self._h, dtype_code(ar), dtype_code(x.dtype),
+            dtype_code(result.dtype), n, _dev_ptr(x), incx, _dev_ptr(y), incy,
+            _dev_ptr(result), _stream_ptr(stream)))
+
     def trsv(self, ar, uplo: int, diag: int, n: int, A: torch.Tensor, lda: int,
              x: torch.Tensor, incx: int, stream=None) -> None:
         assert x.dtype == A.dtype

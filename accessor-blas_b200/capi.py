@@ -49,6 +49,12 @@ SYMBOLS = {
     "accblas_trsv_host": (c_int, [_P, c_int, c_int, c_int, c_int, c_int64, _P,
                                   c_int64, _P, c_int64, _P]),
     "accblas_tune": (c_int, [c_char_p, c_int]),
+    "accblas_peer_export": (c_int, [_P, _P]),
+    "accblas_peer_connect_ipc": (c_int, [_P, c_int, c_int, _P]),
+    "accblas_peer_mailbox": (c_int, [_P, POINTER(_P)]),
+    "accblas_peer_connect_ptrs": (c_int, [_P, c_int, c_int, POINTER(_P), POINTER(c_int)]),
+    "accblas_dot_allreduce": (c_int, [_P, c_int, c_int, c_int, c_int64, _P, c_int64, _P,
+                                      c_int64, _P, _P]),
 }
 
 BASELINE_SYMBOLS = {

@@ -17,7 +17,7 @@ int gemv_impl(Handle*, int ar, int st, std::int64_t m, std::int64_t n,
               cudaStream_t);
 int dot_impl(Handle*, int ar, int st, int res, std::int64_t n, const void* x,
              std::int64_t incx, const void* y, std::int64_t incy, void* result,
-             cudaStream_t);
+             cudaStream_t, const PeerExchange* px = nullptr);
 int trsv_impl(Handle*, int ar, int st, int uplo, int diag, std::int64_t n,
               const void* A, std::int64_t lda, void* x, std::int64_t incx,
               cudaStream_t, long long* trace = nullptr);
@@ -285,6 +285,14 @@ int accblas_destroy(accblas_handle_t handle)
             cudaFree(h->stage[i]);
         }
     }
+    for (int i = 0; i < accblas::kMaxPeers; ++i) {
+        if (h->peer_mailbox[i] && h->peer_is_ipc[i]) {
+            cudaIpcCloseMemHandle(h->peer_mailbox[i]);
+        }
+    }
+    if (h->mailbox) {
+        cudaFree(h->mailbox);
+    }
     delete h;
     return ACCBLAS_OK;
 }
@@ -336,6 +344,168 @@ int accblas_dot(accblas_handle_t handle, accblas_dtype ar, accblas_dtype st,
         return ACCBLAS_ERR_INVALID;
     }
     return accblas::dot_impl(h, ar, st, res, n, x, incx, y, incy, result, s);
+}
+
+// ---- multi-GPU DOT: partials combined inside the kernel over peer memory ----
+static int ensure_mailbox(Handle* h)
+{
+    if (h->mailbox == nullptr) {
+        // plain cudaMalloc: the allocation must be exportable with CUDA IPC
+        ACCBLAS_CUDA(cudaMalloc(&h->mailbox, accblas::kMailboxBytes));
+        ACCBLAS_CUDA(cudaMemset(h->mailbox, 0, accblas::kMailboxBytes));
+        ACCBLAS_CUDA(cudaDeviceSynchronize());
+    }
+    return ACCBLAS_OK;
+}
+
+int accblas_peer_mailbox(accblas_handle_t handle, void** device_ptr)
+{
+    accblas_stream_t stream = nullptr;
+    ACCBLAS_ENTER(handle);
+    (void)s;
+    if (device_ptr == nullptr) {
+        return ACCBLAS_ERR_INVALID;
+    }
+    int rc = ensure_mailbox(h);
+    if (rc != ACCBLAS_OK) {
+        return rc;
+    }
+    *device_ptr = h->mailbox;
+    return ACCBLAS_OK;
+}
+
+int accblas_peer_export(accblas_handle_t handle, void* ipc_handle_64_bytes)
+{
+    accblas_stream_t stream = nullptr;
+    ACCBLAS_ENTER(handle);
+    (void)s;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (ipc_handle_64_bytes == nullptr) {
+        return ACCBLAS_ERR_INVALID;
+    }
+    int rc = ensure_mailbox(h);
+    if (rc != ACCBLAS_OK) {
+        return rc;
+    }
+    cudaIpcMemHandle_t ipc;
+    ACCBLAS_CUDA(cudaIpcGetMemHandle(&ipc, h->mailbox));
+    memcpy(ipc_handle_64_bytes, &ipc, sizeof(ipc));
+    return ACCBLAS_OK;
+}
+
+static int peer_reset(Handle* h, int world, int rank)
+{
+    if (world < 1 || world > accblas::kMaxPeers || rank < 0 || rank >= world) {
+        accblas::set_error("peer connect: world=%d rank=%d (at most %d peers)",
+                           world, rank, accblas::kMaxPeers);
+        return ACCBLAS_ERR_INVALID;
+    }
+    int rc = ensure_mailbox(h);
+    if (rc != ACCBLAS_OK) {
+        return rc;
+    }
+    for (int i = 0; i < accblas::kMaxPeers; ++i) {
+        if (h->peer_mailbox[i] && h->peer_is_ipc[i]) {
+            cudaIpcCloseMemHandle(h->peer_mailbox[i]);
+        }
+        h->peer_mailbox[i] = nullptr;
+        h->peer_is_ipc[i] = false;
+    }
+    // a fresh group starts from a clean mailbox and epoch 0 on every rank
+    ACCBLAS_CUDA(cudaMemset(h->mailbox, 0, accblas::kMailboxBytes));
+    ACCBLAS_CUDA(cudaDeviceSynchronize());
+    h->peer_world = world;
+    h->peer_rank = rank;
+    h->peer_epoch = 0;
+    h->peer_mailbox[rank] = h->mailbox;
+    return ACCBLAS_OK;
+}
+
+int accblas_peer_connect_ipc(accblas_handle_t handle, int world, int rank,
+                             const void* ipc_handles)
+{
+    accblas_stream_t stream = nullptr;
+    ACCBLAS_ENTER(handle);
+    (void)s;
+    if (ipc_handles == nullptr) {
+        return ACCBLAS_ERR_INVALID;
+    }
+    int rc = peer_reset(h, world, rank);
+    if (rc != ACCBLAS_OK) {
+        return rc;
+    }
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            continue;
+        }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, static_cast<const char*>(ipc_handles) + 64 * r, 64);
+        void* mapped = nullptr;
+        ACCBLAS_CUDA(cudaIpcOpenMemHandle(&mapped, ipc,
+                                          cudaIpcMemLazyEnablePeerAccess));
+        h->peer_mailbox[r] = mapped;
+        h->peer_is_ipc[r] = true;
+    }
+    return ACCBLAS_OK;
+}
+
+int accblas_peer_connect_ptrs(accblas_handle_t handle, int world, int rank,
+                              void* const* mailboxes, const int* devices)
+{
+    accblas_stream_t stream = nullptr;
+    ACCBLAS_ENTER(handle);
+    (void)s;
+    if (mailboxes == nullptr || devices == nullptr) {
+        return ACCBLAS_ERR_INVALID;
+    }
+    int rc = peer_reset(h, world, rank);
+    if (rc != ACCBLAS_OK) {
+        return rc;
+    }
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            continue;
+        }
+        if (devices[r] != h->device) {
+            cudaError_t err = cudaDeviceEnablePeerAccess(devices[r], 0);
+            if (err == cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+            } else if (err != cudaSuccess) {
+                return accblas::cuda_fail(err, "cudaDeviceEnablePeerAccess");
+            }
+        }
+        h->peer_mailbox[r] = mailboxes[r];
+    }
+    return ACCBLAS_OK;
+}
+
+int accblas_dot_allreduce(accblas_handle_t handle, accblas_dtype ar,
+                          accblas_dtype st, accblas_dtype res, int64_t n,
+                          const void* x, int64_t incx, const void* y,
+                          int64_t incy, void* result, accblas_stream_t stream)
+{
+    ACCBLAS_ENTER(handle);
+    if (n < 0 || incx < 1 || incy < 1 || !accblas::valid_dtype(res)) {
+        accblas::set_error("dot_allreduce: bad shape");
+        return ACCBLAS_ERR_INVALID;
+    }
+    if (result == nullptr || (n > 0 && (x == nullptr || y == nullptr))) {
+        accblas::set_error("dot_allreduce: null operand");
+        return ACCBLAS_ERR_INVALID;
+    }
+    if (h->peer_world < 1) {
+        accblas::set_error("dot_allreduce: call accblas_peer_connect_* first");
+        return ACCBLAS_ERR_INVALID;
+    }
+    accblas::PeerExchange px;
+    px.world = h->peer_world;
+    px.rank = h->peer_rank;
+    px.epoch = ++h->peer_epoch;
+    for (int r = 0; r < px.world; ++r) {
+        px.mailbox[r] = h->peer_mailbox[r];
+    }
+    return accblas::dot_impl(h, ar, st, res, n, x, incx, y, incy, result, s,
+                             &px);
 }
 
 int accblas_trsv(accblas_handle_t handle, accblas_dtype ar, accblas_dtype st,

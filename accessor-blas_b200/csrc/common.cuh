@@ -28,6 +28,28 @@ struct Handle {
     size_t stage_bytes[4] = {0, 0, 0, 0};
     // bytes of the TRSV progress region currently known to hold the sentinel
     size_t trsv_armed_bytes = 0;
+    // peer exchange (multi-GPU DOT): this GPU's mailbox, the peers' mailboxes
+    // as mapped into this process, and the call counter all ranks share
+    void* mailbox = nullptr;
+    void* peer_mailbox[8] = {};
+    bool peer_is_ipc[8] = {};
+    int peer_world = 0;
+    int peer_rank = 0;
+    unsigned long long peer_epoch = 0;
+};
+
+// What the last CTA of a DOT needs to combine the per-GPU partials itself:
+// every rank writes {value, epoch} into slot [epoch & 1][rank] of EVERY rank's
+// mailbox over NVLink and waits until its own mailbox holds all `world`
+// entries of this epoch; the sum is formed in rank order on every GPU, so all
+// ranks get the same bits whatever the arrival order.  world == 0: disabled.
+constexpr int kMaxPeers = 8;
+constexpr size_t kMailboxBytes = 2 * kMaxPeers * 16;
+struct PeerExchange {
+    int world = 0;
+    int rank = 0;
+    unsigned long long epoch = 0;
+    void* mailbox[kMaxPeers] = {};
 };
 
 // thread-local error message (accblas_last_error)

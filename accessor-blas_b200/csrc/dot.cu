@@ -84,11 +84,67 @@ __device__ __forceinline__ void store_result(void* result, int res_dtype, Ar v)
     }
 }
 
+__device__ __forceinline__ unsigned long long dot_globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Fused all-reduce of the per-GPU partials (one thread per peer): store my
+// partial into every peer's mailbox (P2P stores over NVLink), then wait for the
+// peer's entry in mine.  Returns the sum in rank order (valid in thread 0).
+// A peer that never shows up (2 s) yields NaN instead of a hung GPU.
+template <typename Ar>
+__device__ __forceinline__ Ar peer_allreduce(Ar mine, const PeerExchange& px)
+{
+    __shared__ double peer_vals[kMaxPeers];
+    __shared__ Ar mine_s;
+    if (threadIdx.x == 0) {
+        mine_s = mine;
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < px.world) {
+        const int half = static_cast<int>(px.epoch & 1ull) * kMaxPeers;
+        const double payload = static_cast<double>(mine_s);  // exact for float
+        volatile unsigned long long* out =
+            static_cast<volatile unsigned long long*>(px.mailbox[t]) +
+            2 * (half + px.rank);
+        out[0] = static_cast<unsigned long long>(__double_as_longlong(payload));
+        __threadfence_system();  // value before flag, system scope (peer GPU)
+        out[1] = px.epoch;
+        volatile unsigned long long* in =
+            static_cast<volatile unsigned long long*>(px.mailbox[px.rank]) +
+            2 * (half + t);
+        const unsigned long long t0 = dot_globaltimer_ns();
+        bool ok = true;
+        while (in[1] != px.epoch) {
+            if (dot_globaltimer_ns() - t0 > 2000000000ull) {
+                ok = false;
+                break;
+            }
+        }
+        __threadfence_system();  // flag before value
+        peer_vals[t] = ok ? __longlong_as_double(static_cast<long long>(in[0]))
+                          : __longlong_as_double(0x7ff8000000000000LL);
+    }
+    __syncthreads();
+    Ar total = Ar{};
+    if (t == 0) {
+        for (int r = 0; r < px.world; ++r) {
+            total += static_cast<Ar>(peer_vals[r]);
+        }
+    }
+    return total;
+}
+
 // Second pass + epilogue shared by both first-pass kernels.
 template <typename Ar, int BLOCK>
 __device__ __forceinline__ void finish_dot(Ar local, Ar* partials,
                                            unsigned* counter, void* result,
-                                           int res_dtype, Ar* scratch)
+                                           int res_dtype, Ar* scratch,
+                                           const PeerExchange& px)
 {
     __shared__ bool is_last;
     const Ar total = block_sum(local, scratch);
@@ -109,7 +165,10 @@ __device__ __forceinline__ void finish_dot(Ar local, Ar* partials,
     for (unsigned i = threadIdx.x; i < gridDim.x; i += BLOCK) {
         v += __ldcg(partials + i);
     }
-    const Ar sum = block_sum(v, scratch);
+    Ar sum = block_sum(v, scratch);
+    if (px.world > 1) {
+        sum = peer_allreduce(sum, px);
+    }
     if (threadIdx.x == 0) {
         store_result(result, res_dtype, sum);
         *counter = 0u;  // re-arm for the next call on this handle
@@ -121,7 +180,7 @@ template <typename St, typename Ar, int BLOCK, int UNROLL>
 __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     const St* __restrict__ x, const St* __restrict__ y, std::int64_t n,
     Ar* __restrict__ partials, unsigned* __restrict__ counter,
-    void* __restrict__ result, int res_dtype)
+    void* __restrict__ result, int res_dtype, const PeerExchange px)
 {
     constexpr int VEC = vec_traits<St>::elems;
     constexpr std::int64_t TILE = std::int64_t{BLOCK} * VEC * UNROLL;
@@ -193,7 +252,8 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
         local += v[0];
     }
     local += tail;
-    finish_dot<Ar, BLOCK>(local, partials, counter, result, res_dtype, scratch);
+    finish_dot<Ar, BLOCK>(local, partials, counter, result, res_dtype, scratch,
+                          px);
 }
 
 // Any stride / alignment: scalar loads, 64-bit indices (the reference's plain
@@ -202,7 +262,8 @@ template <typename St, typename Ar, int BLOCK>
 __global__ __launch_bounds__(BLOCK) void dot_strided_kernel(
     const St* __restrict__ x, std::int64_t incx, const St* __restrict__ y,
     std::int64_t incy, std::int64_t n, Ar* __restrict__ partials,
-    unsigned* __restrict__ counter, void* __restrict__ result, int res_dtype)
+    unsigned* __restrict__ counter, void* __restrict__ result, int res_dtype,
+    const PeerExchange px)
 {
     __shared__ Ar scratch[kWarp];
     Ar acc0 = Ar{}, acc1 = Ar{};
@@ -218,12 +279,13 @@ __global__ __launch_bounds__(BLOCK) void dot_strided_kernel(
         acc0 = pair_fma<Ar, St>::apply(x[i * incx], y[i * incy], acc0);
     }
     finish_dot<Ar, BLOCK>(acc0 + acc1, partials, counter, result, res_dtype,
-                          scratch);
+                          scratch, px);
 }
 
 template <typename St, typename Ar, int BLOCK, int UNROLL>
 int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
-                  void* result, int res, int ctas_per_sm, cudaStream_t stream)
+                  void* result, int res, int ctas_per_sm, cudaStream_t stream,
+                  const PeerExchange& px)
 {
     constexpr int VEC = vec_traits<St>::elems;
     constexpr std::int64_t TILE = std::int64_t{BLOCK} * VEC * UNROLL;
@@ -256,7 +318,7 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
     kernel<<<static_cast<unsigned>(grid), BLOCK, 0, stream>>>(
         static_cast<const St*>(x), static_cast<const St*>(y), n,
         static_cast<Ar*>(payload(h)), control_words(h) + kCtlDotCounter,
-        result, res);
+        result, res, px);
     ACCBLAS_CUDA(cudaGetLastError());
     return ACCBLAS_OK;
 }
@@ -264,7 +326,7 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
 template <typename St, typename Ar>
 int launch_dot(Handle* h, std::int64_t n, const void* x, std::int64_t incx,
                const void* y, std::int64_t incy, void* result, int res,
-               cudaStream_t stream)
+               cudaStream_t stream, const PeerExchange& px)
 {
     const bool aligned =
         ((reinterpret_cast<std::uintptr_t>(x) |
@@ -275,13 +337,13 @@ int launch_dot(Handle* h, std::int64_t n, const void* x, std::int64_t incx,
         switch (unroll) {
         case 2:
             return launch_stream<St, Ar, 256, 2>(h, n, x, y, result, res, cps,
-                                                 stream);
+                                                 stream, px);
         case 8:
             return launch_stream<St, Ar, 256, 8>(h, n, x, y, result, res, cps,
-                                                 stream);
+                                                 stream, px);
         default:
             return launch_stream<St, Ar, 256, 4>(h, n, x, y, result, res, cps,
-                                                 stream);
+                                                 stream, px);
         }
     }
     constexpr int BLOCK = 256;
@@ -302,7 +364,7 @@ int launch_dot(Handle* h, std::int64_t n, const void* x, std::int64_t incx,
         <<<static_cast<unsigned>(grid), BLOCK, 0, stream>>>(
             static_cast<const St*>(x), incx, static_cast<const St*>(y), incy, n,
             static_cast<Ar*>(payload(h)), control_words(h) + kCtlDotCounter,
-            result, res);
+            result, res, px);
     ACCBLAS_CUDA(cudaGetLastError());
     return ACCBLAS_OK;
 }
@@ -311,12 +373,14 @@ int launch_dot(Handle* h, std::int64_t n, const void* x, std::int64_t incx,
 
 int dot_impl(Handle* h, int ar, int st, int res, std::int64_t n, const void* x,
              std::int64_t incx, const void* y, std::int64_t incy, void* result,
-             cudaStream_t stream)
+             cudaStream_t stream, const PeerExchange* px_or_null)
 {
+    const PeerExchange px = px_or_null ? *px_or_null : PeerExchange{};
     return dispatch_ar_st(ar, st, [&](auto st_tag, auto ar_tag) {
         using St = decltype(st_tag);
         using Ar = decltype(ar_tag);
-        return launch_dot<St, Ar>(h, n, x, incx, y, incy, result, res, stream);
+        return launch_dot<St, Ar>(h, n, x, incx, y, incy, result, res, stream,
+                                  px);
     });
 }
 

@@ -9,7 +9,9 @@ One process per GPU, `torch.distributed` (NCCL over NVLink) for the plumbing.
   DOT   the index range is split into contiguous, 16-byte aligned chunks; each
         rank produces one partial in the arithmetic type with the
         deterministic two-pass kernel; ONE single-element all-reduce combines
-        them; the cast to the result type happens after the reduction.
+        them; the cast to the result type happens after the reduction.  With
+        fused=True the exchange happens inside the DOT kernel over peer memory
+        (accblas_dot_allreduce): no collective call at all.
   TRSV  does not shard (one dependency chain): replicas only.
 
 The reference has no multi-device code at all (device 0 is hard-coded,
@@ -93,18 +95,53 @@ class ShardedGemv:
         return y_local
 
 
-class ShardedDot:
-    """Range-sharded dot product with one all-reduce of the partials."""
+def connect_peers(handle, group=None) -> bool:
+    """One-time set-up of the in-kernel all-reduce: every rank exports the CUDA
+    IPC handle of its mailbox, the handles are gathered in rank order and each
+    rank maps its peers' mailboxes.  Returns False (nothing connected) when
+    there is a single rank, more than 8, or no CUDA process group."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return False
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world < 2 or world > 8:
+        return False
+    mine = handle.peer_export()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine, group=group)
+    handle.peer_connect_ipc(world, rank, b"".join(gathered))
+    dist.barrier(group=group)  # nobody publishes into a mailbox not yet mapped
+    return True
 
-    def __init__(self, handle, ar, n: int, group=None):
+
+class ShardedDot:
+    """Range-sharded dot product.
+
+    fused=False: per-rank partial + ONE single-element NCCL all-reduce.
+    fused=True : the kernel's last CTA exchanges the partials with the peers
+                 over NVLink (P2P stores into every rank's mailbox) and sums
+                 them in rank order -- one launch per rank, no collective
+                 call, identical bits on all ranks (`connect_peers` first).
+    """
+
+    def __init__(self, handle, ar, n: int, group=None, fused: bool = False):
         self.handle, self.ar, self.n, self.group = handle, ar, n, group
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.first, self.count = range_partition(n, world, rank)
         self._partial: Optional[torch.Tensor] = None
+        self.fused = bool(fused) and world > 1
+        if self.fused and not connect_peers(handle, group):
+            self.fused = False
 
     def __call__(self, x_local: torch.Tensor, y_local: torch.Tensor,
                  res_dtype: torch.dtype, stream=None) -> torch.Tensor:
+        if self.fused:
+            if self._partial is None or self._partial.dtype != res_dtype:
+                self._partial = torch.zeros(1, dtype=res_dtype, device=x_local.device)
+            self.handle.dot_allreduce(self.ar, self.count, x_local, 1, y_local, 1,
+                                      self._partial, stream)
+            return self._partial
         if self._partial is None:
             self._partial = torch.zeros(1, dtype=self.ar, device=x_local.device)
         self.handle.dot(self.ar, self.count, x_local, 1, y_local, 1,

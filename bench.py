@@ -498,18 +498,30 @@ def run_accblas_arm(args):
     yd = torch.empty(d_count, dtype=st, device=dev)
     h.fill_uniform(1, d_count, xd, d_count, 42, d_first)
     h.fill_uniform(1, d_count, yd, d_count, 42, nd_total + d_first)
-    sdot = sharded.ShardedDot(h, ar, nd_total)
+    # partials combined inside the DOT kernel over peer memory (NVLink); the
+    # NCCL single-element all-reduce is timed next to it
+    sdot = sharded.ShardedDot(h, ar, nd_total, fused=True)
     dot_ms = time_launches(lambda: sdot(xd, yd, torch.float32), args.steps, args.warmup,
                            torch, barrier)
+    nccl_ms = None
     if world > 1:
         t = torch.tensor([dot_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dot_ms = float(t.item())
+        ndot = sharded.ShardedDot(h, ar, nd_total, fused=False)
+        nccl_ms = time_launches(lambda: ndot(xd, yd, torch.float32), args.steps,
+                                args.warmup, torch, barrier)
+        t = torch.tensor([nccl_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nccl_ms = float(t.item())
     extra["dot_sharded"] = {
-        "workload": f"DOT n=2^28 per GPU (total {nd_total}), Acc<fp64,fp32>, "
-                    "one 1-element all-reduce per step" + ("" if world > 1 else " (skipped at N=1)"),
+        "workload": f"DOT n=2^28 per GPU (total {nd_total}), Acc<fp64,fp32>, " +
+                    (("partials exchanged inside the kernel over peer memory"
+                      if sdot.fused else "one 1-element NCCL all-reduce per step")
+                     if world > 1 else "single rank"),
         "ms_per_step": dot_ms,
         "GBps": dot_bytes(nd_total, s, 4) / (dot_ms * 1e-3) / 1e9,
+        "ms_per_step_nccl_allreduce": nccl_ms,
         "result": float(sdot(xd, yd, torch.float32).item())}
     del xd, yd
 
@@ -597,7 +609,7 @@ def run_config5(args, ab, sharded, h, torch, dist, world, rank, dev, barrier, pe
     yd = torch.empty(d_count, dtype=st, device=dev)
     h.fill_uniform(1, d_count, xd, d_count, 42, d_first)
     h.fill_uniform(1, d_count, yd, d_count, 42, nd + d_first)
-    sdot = sharded.ShardedDot(h, ar, nd)
+    sdot = sharded.ShardedDot(h, ar, nd, fused=True)
     dot_ms = time_launches(lambda: sdot(xd, yd, torch.float32), steps, warmup, torch, barrier)
     if world > 1:
         t = torch.tensor([dot_ms], dtype=torch.float64, device=dev)
@@ -623,7 +635,9 @@ def run_config5(args, ab, sharded, h, torch, dist, world, rank, dev, barrier, pe
                       "dot": {"n": nd, "ms_per_step": dot_ms,
                               "GBps": dot_bytes(nd, s, 4) / (dot_ms * 1e-3) / 1e9,
                               "result": dot_value,
-                              "collective": "1-element all_reduce(SUM) per call"
+                              "collective": ("in-kernel exchange over peer memory"
+                                             if sdot.fused else
+                                             "1-element all_reduce(SUM) per call")
                               if world > 1 else "none (N=1)"}},
         }), flush=True)
     if world > 1:

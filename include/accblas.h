@@ -95,6 +95,29 @@ int accblas_dot(accblas_handle_t handle, accblas_dtype ar, accblas_dtype st,
                 const void* y, int64_t incy, void* result,
                 accblas_stream_t stream);
 
+/* Multi-GPU DOT (BASELINE.json config 5; the reference is single-device,
+ * cuda/dot_kernels.cuh:33): every rank calls accblas_dot_allreduce on its own
+ * index range; the kernel's last CTA writes the rank's partial (in `ar`) into
+ * every peer's mailbox over NVLink, waits for the peers' partials in its own
+ * mailbox and sums them in rank order, so *result (as `res`) is the dot
+ * product of the whole vectors on every rank, with identical bits on all of
+ * them -- one launch per rank, no separate collective.  At most 8 ranks.
+ * Set-up, once per group: either (one process per GPU) every rank calls
+ * accblas_peer_export, the 64-byte CUDA IPC handles are gathered in rank
+ * order and passed to accblas_peer_connect_ipc; or (one process, several
+ * handles) accblas_peer_mailbox + accblas_peer_connect_ptrs.  All ranks must
+ * issue the same sequence of accblas_dot_allreduce calls. */
+int accblas_peer_export(accblas_handle_t handle, void* ipc_handle_64_bytes);
+int accblas_peer_connect_ipc(accblas_handle_t handle, int world, int rank,
+                             const void* ipc_handles /* world x 64 bytes */);
+int accblas_peer_mailbox(accblas_handle_t handle, void** device_ptr);
+int accblas_peer_connect_ptrs(accblas_handle_t handle, int world, int rank,
+                              void* const* mailboxes, const int* devices);
+int accblas_dot_allreduce(accblas_handle_t handle, accblas_dtype ar,
+                          accblas_dtype st, accblas_dtype res, int64_t n,
+                          const void* x, int64_t incx, const void* y,
+                          int64_t incy, void* result, accblas_stream_t stream);
+
 /* In-place triangular solve T * x_out = x_in with T the `uplo` triangle of
  * the row-major n x n matrix A (unit or stored diagonal).  x is read and
  * written as `st`; every solved entry is rounded to `st` before later rows

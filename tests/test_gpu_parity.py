@@ -354,6 +354,63 @@ def test_trsv_repeated_calls_and_strided_x(oracle, ab, handle):
 
 
 # ---------------------------------------------------------------------------
+# multi-GPU DOT with the all-reduce inside the kernel (peer mailboxes)
+# ---------------------------------------------------------------------------
+def _peer_group(ab, devices):
+    handles = [ab.Handle(d) for d in devices]
+    boxes = [h.peer_mailbox() for h in handles]
+    for r, h in enumerate(handles):
+        h.peer_connect_ptrs(len(devices), r, boxes, devices)
+    return handles
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("ar,st", [(torch.float64, torch.float32), (torch.float32, torch.float16),
+                                   (torch.float64, torch.float64)])
+def test_dot_allreduce_in_kernel_matches_rank_order_sum(oracle, ab, world, ar, st):
+    """`world` ranks as handles of ONE process (all on the visible devices,
+    round robin; several ranks may share a GPU -- their kernels then run one
+    after the other and the earlier one's last CTA waits for the later one).
+    Every rank must return the rank-order sum of the per-rank partials, with
+    identical bits, call after call (the mailbox alternates between two epochs)."""
+    ndev = torch.cuda.device_count()
+    devices = [r % ndev for r in range(world)]
+    handles = _peer_group(ab, devices)
+    n = 1_000_003
+    x = stored(oracle, n, st, seed=21)
+    y = stored(oracle, n, st, seed=22)
+    from accessor_blas_b200.sharded import range_partition
+    parts = [range_partition(n, world, r) for r in range(world)]
+    streams = [torch.cuda.Stream(device=d) for d in devices]
+    xs, ys, outs, partials = [], [], [], []
+    for r, (first, count) in enumerate(parts):
+        with torch.cuda.device(devices[r]):
+            xs.append(torch.from_numpy(x[first:first + count].copy()).cuda(devices[r]))
+            ys.append(torch.from_numpy(y[first:first + count].copy()).cuda(devices[r]))
+            outs.append(torch.zeros(1, dtype=ar, device=f"cuda:{devices[r]}"))
+            p = torch.zeros(1, dtype=ar, device=f"cuda:{devices[r]}")
+            handles[r].dot(ar, count, xs[r], 1, ys[r], 1, p)
+            partials.append(p.cpu())
+    want = torch.zeros(1, dtype=ar)
+    for p in partials:  # rank order, in the arithmetic type
+        want = want + p
+    for call in range(3):
+        for r, (first, count) in enumerate(parts):
+            with torch.cuda.device(devices[r]):
+                outs[r].zero_()
+                handles[r].dot_allreduce(ar, count, xs[r], 1, ys[r], 1, outs[r], streams[r])
+        for d in set(devices):
+            torch.cuda.synchronize(d)
+        for r in range(world):
+            got = outs[r].cpu()
+            assert torch.equal(got, want), (call, r, got.item(), want.item())
+    exact = oracle.exact_dot(x, y)
+    scale = float(np.abs(x.astype(np.float64) * y.astype(np.float64)).sum())
+    tol = 5e-14 if ar == torch.float64 else 2e-5
+    assert abs(want.item() - exact) <= tol * scale
+
+
+# ---------------------------------------------------------------------------
 # host-buffer entry points (the e2e path of bench.py)
 # ---------------------------------------------------------------------------
 def test_host_entry_points(oracle, ab, handle):
