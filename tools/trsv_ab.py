@@ -3,7 +3,12 @@
     python tools/trsv_ab.py [old.so]
 
 Latency-bound kernels differ by tens of percent between gpurun boxes, so two
-versions are only ever compared inside one process, interleaved.
+versions are only ever compared inside one process, interleaved.  The "old"
+library is built from an earlier commit, e.g.
+    git archive <commit> accessor-blas_b200/csrc include | tar -x -C /tmp/old
+    nvcc -std=c++17 -O3 -Xcompiler -fPIC -I/tmp/old/include -I/tmp/old/accessor-blas_b200/csrc \
+         -gencode arch=compute_100a,code=sm_100a -shared -cudart static \
+         -o tools/micro/libaccblas_old.so /tmp/old/accessor-blas_b200/csrc/{capi,dot,gemv,trsv,convert_fill}.cu
 """
 import ctypes
 import sys
