@@ -745,6 +745,10 @@ int accblas_tune(const char* key, int value)
         t.gemv_stages = value;
     } else if (!strcmp(key, "gemv_taper")) {
         t.gemv_taper = value;
+    } else if (!strcmp(key, "dot_pdl")) {
+        t.dot_pdl = value;
+    } else if (!strcmp(key, "gemv_pdl")) {
+        t.gemv_pdl = value;
     } else if (!strcmp(key, "gemv_pipe")) {
         t.gemv_pipe = value;
     } else if (!strcmp(key, "gemv_intwords")) {

@@ -180,11 +180,31 @@ template <typename St, typename Ar, int BLOCK, int UNROLL>
 __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     const St* __restrict__ x, const St* __restrict__ y, std::int64_t n,
     Ar* __restrict__ partials, unsigned* __restrict__ counter,
-    void* __restrict__ result, int res_dtype, const PeerExchange px)
+    void* __restrict__ result, int res_dtype, const PeerExchange px, int pdl)
 {
     constexpr int VEC = vec_traits<St>::elems;
     constexpr std::int64_t TILE = std::int64_t{BLOCK} * VEC * UNROLL;
     __shared__ Ar scratch[kWarp];
+    if (pdl) {
+        // programmatic dependent launch (see gemv.cu): the next kernel of the
+        // stream may become resident while this grid drains; nothing but L2
+        // prefetches of the first tile happens before the predecessor is done
+        asm volatile("griddepcontrol.launch_dependents;");
+        if (static_cast<std::int64_t>(blockIdx.x) < n / TILE) {
+            const std::int64_t first =
+                blockIdx.x * TILE + std::int64_t{threadIdx.x} * VEC;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if ((threadIdx.x & 7) == 0) {  // one request per 128-byte line
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                        x + first + std::int64_t{u} * BLOCK * VEC));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                        y + first + std::int64_t{u} * BLOCK * VEC));
+                }
+            }
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
 
     const std::int64_t num_tiles = n / TILE;
     // fp32 arithmetic: one accumulator per (vector, element) slot, so a chain
@@ -315,11 +335,20 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
     if (rc != ACCBLAS_OK) {
         return rc;
     }
-    kernel<<<static_cast<unsigned>(grid), BLOCK, 0, stream>>>(
-        static_cast<const St*>(x), static_cast<const St*>(y), n,
-        static_cast<Ar*>(payload(h)), control_words(h) + kCtlDotCounter,
-        result, res, px);
-    ACCBLAS_CUDA(cudaGetLastError());
+    const int pdl = tuning().dot_pdl;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(BLOCK);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    ACCBLAS_CUDA(cudaLaunchKernelEx(
+        &cfg, kernel, static_cast<const St*>(x), static_cast<const St*>(y), n,
+        static_cast<Ar*>(payload(h)), control_words(h) + kCtlDotCounter, result,
+        res, px, pdl));
     return ACCBLAS_OK;
 }
 

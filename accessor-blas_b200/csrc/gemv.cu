@@ -615,8 +615,16 @@ __global__ __launch_bounds__(RG* COLW* kWarp, MINB)
 void gemv_stream_kernel(
     std::int64_t m, std::int64_t n, Ar alpha, const St* __restrict__ A,
     std::int64_t lda, const St* __restrict__ x, Ar beta, St* __restrict__ y,
-    std::int64_t incy, std::int64_t b_full, std::int64_t b_half)
+    std::int64_t incy, std::int64_t b_full, std::int64_t b_half, int pdl)
 {
+    // Programmatic dependent launch: let the NEXT kernel of the stream become
+    // resident as soon as every CTA of this grid has started (it fills the SM
+    // slots our last wave leaves empty), and do not touch anything a previous
+    // kernel may still be writing before griddepcontrol.wait.  Only requests
+    // into L2 (always coherent) are issued ahead of the wait.
+    if (pdl) {
+        asm volatile("griddepcontrol.launch_dependents;");
+    }
     constexpr int HALF = ROWS >= 2 ? ROWS / 2 : 1;
     constexpr int QUARTER = ROWS >= 4 ? ROWS / 4 : 1;
     __shared__ Ar part[RG][COLW][ROWS];
@@ -639,6 +647,23 @@ void gemv_stream_kernel(
     }
 
     const std::int64_t b = blockIdx.x;
+    if (pdl) {
+        // first chunk of this warp's rows -> L2 while the predecessor drains
+        constexpr int VEC = vec_traits<St>::elems;
+        std::int64_t row0 = (b < b_full) ? (b * RG + rg) * ROWS : m;
+        if (row0 < m && static_cast<std::int64_t>(cw + 1) * kWarp * VEC * UNROLL <= n) {
+            const St* p0 = A + row0 * lda +
+                           static_cast<std::int64_t>(cw) * kWarp * VEC * UNROLL;
+            const int r = lane >> 3;  // ROWS <= 4 rows x 8 lines of 128 bytes
+            const int line = lane & 7;
+            if (r < ROWS && row0 + r < m &&
+                line * 128 < kWarp * 16 * UNROLL) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                    reinterpret_cast<const char*>(p0 + r * lda) + line * 128));
+            }
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     if (b < b_full) {
         const std::int64_t row0 = (b * RG + rg) * ROWS;
         gemv_row_group<St, Ar, ROWS, ROWS, UNROLL, COLW, PIPE, IW>(
@@ -1039,9 +1064,19 @@ int launch_stream(Handle* h, std::int64_t m, std::int64_t n, Ar alpha,
         set_error("gemv: too many rows (%lld)", static_cast<long long>(m));
         return ACCBLAS_ERR_INVALID;
     }
-    kernel<<<static_cast<unsigned>(grid), RG * COLW * kWarp, smem, stream>>>(
-        m, n, alpha, A, lda, x, beta, y, incy, b_full, b_half);
-    ACCBLAS_CUDA(cudaGetLastError());
+    const int pdl = tuning().gemv_pdl;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(RG * COLW * kWarp);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    ACCBLAS_CUDA(cudaLaunchKernelEx(&cfg, kernel, m, n, alpha, A, lda, x, beta,
+                                    y, incy, b_full, b_half, pdl));
     return ACCBLAS_OK;
 }
 

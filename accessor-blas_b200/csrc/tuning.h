@@ -8,11 +8,13 @@ namespace accblas {
 struct Tuning {
     int dot_unroll = 4;        // 128-bit vectors of each operand in flight per thread
     int dot_ctas_per_sm = 0;   // grid = SMs * this (256 threads per CTA); 0 = all that are resident
+    int dot_pdl = 1;           // programmatic dependent launch for back-to-back DOTs
     int gemv_unroll = 2;       // vectors per row in flight per lane
     int gemv_variant = 0;      // 0 = auto, 2 = CTA-per-2-rows, 3 = CTA-per-row, 4 = CTA-per-4-rows, 5 = CTA-per-8-rows
     int gemv_ctas_per_sm = 0;  // 0 = all row groups as separate CTAs
     int gemv_pipe = -1;        // default GEMV shape: -1 = per pair, 0 = plain loop, 1 = register pipeline, 3 / 4 = cp.async ring depth
     int gemv_intwords = 2;     // Acc<fp64,fp16>: words per 128-bit vector widened on the integer pipes (rest: F2F)
+    int gemv_pdl = 1;          // programmatic dependent launch: back-to-back GEMVs overlap tail and ramp
     int gemv_taper = 1;        // shorter row groups at the end of the grid
     int gemv_stages = 0;       // 0 = register path, 2..4 = bulk-copy ring depth
     int trsv_whole_block_spin = 1;  // TRSV: a caught-up CTA waits for a whole x block (1) or 32 entries at a time (0)

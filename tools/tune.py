@@ -118,6 +118,68 @@ if "trsv" in which:
                 print(key, f"{ms * 1e3:8.1f} us", flush=True)
         del T
 
+if "b2b" in which:
+    # back-to-back launches on one stream (what bench.py's `value` and an
+    # iterative solver see): programmatic dependent launch on / off
+    m = k = 16384
+    for st in (torch.float32, torch.float16, torch.float64):
+        A = torch.empty(m * k, dtype=st, device=dev)
+        x = torch.empty(k, dtype=st, device=dev)
+        y = torch.zeros(m, dtype=st, device=dev)
+        h.fill_uniform(m, k, A, k, 42, 0)
+        h.fill_uniform(k, 1, x, 1, 42, m * k)
+        for ar in (torch.float64, torch.float32):
+            for pdl in (0, 1, 0, 1):
+                ab.tune("gemv_pdl", pdl)
+                for _ in range(5):
+                    h.gemv(ar, m, k, 1.0, A, k, x, 1, 0.0, y, 1)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda._sleep(400_000)
+                e0.record()
+                for _ in range(50):
+                    h.gemv(ar, m, k, 1.0, A, k, x, 1, 0.0, y, 1)
+                e1.record()
+                e1.synchronize()
+                ms = e0.elapsed_time(e1) / 50
+                gbs = gemv_bytes(m, k, A.element_size()) / ms / 1e6
+                key = f"gemv b2b Acc<{NAME[ar]},{NAME[st]}> pdl={pdl}"
+                while key in results:
+                    key += " (repeat)"
+                results[key] = round(gbs, 1)
+                print(key, f"{ms * 1e3:8.1f} us/call {gbs:8.1f} GB/s", flush=True)
+        del A
+    ab.tune("gemv_pdl", 1)
+    n = 2 ** 28
+    for st in (torch.float32, torch.float16, torch.float64):
+        x = torch.empty(n, dtype=st, device=dev)
+        y = torch.empty(n, dtype=st, device=dev)
+        h.fill_uniform(1, n, x, n, 42, 0)
+        h.fill_uniform(1, n, y, n, 42, n)
+        for ar in (torch.float64, torch.float32):
+            res = torch.zeros(1, dtype=ar, device=dev)
+            for pdl in (0, 1, 0, 1):
+                ab.tune("dot_pdl", pdl)
+                for _ in range(5):
+                    h.dot(ar, n, x, 1, y, 1, res)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda._sleep(400_000)
+                e0.record()
+                for _ in range(50):
+                    h.dot(ar, n, x, 1, y, 1, res)
+                e1.record()
+                e1.synchronize()
+                ms = e0.elapsed_time(e1) / 50
+                gbs = dot_bytes(n, x.element_size(), res.element_size()) / ms / 1e6
+                key = f"dot b2b Acc<{NAME[ar]},{NAME[st]}> pdl={pdl}"
+                while key in results:
+                    key += " (repeat)"
+                results[key] = round(gbs, 1)
+                print(key, f"{ms * 1e3:8.1f} us/call {gbs:8.1f} GB/s", flush=True)
+        del x, y
+    ab.tune("dot_pdl", 1)
+
 out = ROOT / "gpurun_out"
 out.mkdir(exist_ok=True)
 (out / "tune.json").write_text(json.dumps(results, indent=1))
