@@ -181,12 +181,13 @@ struct ChunkOps {
     // last, partial chunk: whole vectors while they fit, then scalars
     static __device__ __forceinline__ void partial(
         const St* const (&row)[ROWS], const St* __restrict__ x,
-        std::int64_t c0, std::int64_t n, int lane, Ar (&acc)[ROWS][SLOTS])
+        std::int64_t c0, std::int64_t n, int lane, Ar (&acc)[ROWS][SLOTS],
+        bool aligned16 = true)
     {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const std::int64_t col = c0 + (u * kWarp + lane) * VEC;
-            if (col + VEC <= n) {
+            if (aligned16 && col + VEC <= n) {
                 Ar xv[VEC];
                 unpack_all<Ar, St>(ldg_cached_128(x + col), xv);
 #pragma unroll
@@ -199,7 +200,8 @@ struct ChunkOps {
                     }
                 }
             } else {
-                for (std::int64_t c = col; c < n; ++c) {
+                const std::int64_t c_end = (col + VEC < n) ? col + VEC : n;
+                for (std::int64_t c = col; c < c_end; ++c) {
                     const Ar xv = to_ar<Ar, St>(x[c]);
 #pragma unroll
                     for (int r = 0; r < ROWS; ++r) {
@@ -368,7 +370,13 @@ struct BatchOps {
 // so "has my data arrived" is a per-thread cp.async.wait_group -- no barrier,
 // no mbarrier, no producer lane -- and the bytes in flight per warp are
 // (STAGES - 1) x (ROWS + 1) x 512, independent of the register budget.
-template <typename Ar, typename St, int ROWS, bool FAST, int IW, int STAGES>
+// CB = bytes per cp.async (16, 8 or 4): operands that are only 8- or 4-byte
+// aligned (a row stride that is not a multiple of 16 bytes, e.g. fp16 rows of
+// the reference driver's default stride 24500) are copied in 8- or 4-byte
+// pieces into the SAME 16-byte shared-memory slots, so everything after the
+// copy is unchanged -- no scalar kernel, no per-row peeling.
+template <typename Ar, typename St, int ROWS, bool FAST, int IW, int STAGES,
+          int CB = 16>
 struct AsyncOps {
     using B = BatchOps<Ar, St, ROWS, FAST, IW>;
     static constexpr int VEC = B::VEC;
@@ -378,16 +386,25 @@ struct AsyncOps {
     static __device__ __forceinline__ void copy16_stream(unsigned dst,
                                                          const void* src)
     {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
-                     "l"(src)
-                     : "memory");
+        if constexpr (CB == 16) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                         "l"(src)
+                         : "memory");
+        } else {
+            copy16_cached(dst, src);  // pieces below 16 bytes exist as .ca only
+        }
     }
     static __device__ __forceinline__ void copy16_cached(unsigned dst,
                                                          const void* src)
     {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst),
-                     "l"(src)
-                     : "memory");
+        const char* s8 = static_cast<const char*>(src);
+#pragma unroll
+        for (int i = 0; i < 16 / CB; ++i) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(
+                             dst + i * CB),
+                         "l"(s8 + i * CB), "n"(CB)
+                         : "memory");
+        }
     }
     static __device__ __forceinline__ void commit()
     {
@@ -489,7 +506,7 @@ __device__ __forceinline__ void write_row(St* y, std::int64_t idx, Ar alpha,
 // One row group of R rows: the COLW warps that share it walk the column chunks,
 // reduce and write.  `part` is the CTA's [RG][COLW][MAXR] staging array.
 template <typename St, typename Ar, int R, int MAXR, int UNROLL, int COLW,
-          int PIPE, int IW>
+          int PIPE, int IW, int CB>
 __device__ __forceinline__ void gemv_row_group(
     std::int64_t m, std::int64_t n, Ar alpha, const St* __restrict__ A,
     std::int64_t lda, const St* __restrict__ x, Ar beta, St* __restrict__ y,
@@ -526,7 +543,7 @@ __device__ __forceinline__ void gemv_row_group(
         const std::int64_t full_chunks = n / CHUNK;
         __half2 chk = __float2half2_rn(0.0f);
         if constexpr (PIPE >= 2 && UNROLL == 2) {
-            AsyncOps<Ar, St, R, FAST, IW, PIPE>::template stream<COLW>(
+            AsyncOps<Ar, St, R, FAST, IW, PIPE, CB>::template stream<COLW>(
                 row, x, full_chunks, cw, lane, part_acc, chk, ring);
         } else if constexpr (PIPE == 1 && UNROLL == 2) {
             // same chunk ownership and the same accumulator per (row, vector
@@ -551,12 +568,18 @@ __device__ __forceinline__ void gemv_row_group(
                     }
                 }
                 for (std::int64_t k = cw; k < full_chunks; k += COLW) {
-                    ExactOps::full(row, x, k * CHUNK, lane, part_acc, chk);
+                    if constexpr (CB == 16) {
+                        ExactOps::full(row, x, k * CHUNK, lane, part_acc, chk);
+                    } else {
+                        ExactOps::partial(row, x, k * CHUNK, n, lane, part_acc,
+                                          false);
+                    }
                 }
             }
         }
         if (full_chunks % COLW == cw && full_chunks * CHUNK < n) {
-            Ops::partial(row, x, full_chunks * CHUNK, n, lane, part_acc);
+            Ops::partial(row, x, full_chunks * CHUNK, n, lane, part_acc,
+                         CB == 16);
         }
     }
 
@@ -610,7 +633,8 @@ __device__ __forceinline__ void gemv_row_group(
 // uniform shape at 16384^2 fp32: 11 us of a 164 us kernel).  The size class is
 // uniform per CTA, so each class runs its own unpredicated instantiation.
 template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW,
-          int MINB = (ROWS * UNROLL <= 8) ? 3 : 1, int PIPE = 0, int IW = 2>
+          int MINB = (ROWS * UNROLL <= 8) ? 3 : 1, int PIPE = 0, int IW = 2,
+          int CB = 16>
 __global__ __launch_bounds__(RG* COLW* kWarp, MINB)
 void gemv_stream_kernel(
     std::int64_t m, std::int64_t n, Ar alpha, const St* __restrict__ A,
@@ -666,17 +690,17 @@ void gemv_stream_kernel(
     }
     if (b < b_full) {
         const std::int64_t row0 = (b * RG + rg) * ROWS;
-        gemv_row_group<St, Ar, ROWS, ROWS, UNROLL, COLW, PIPE, IW>(
+        gemv_row_group<St, Ar, ROWS, ROWS, UNROLL, COLW, PIPE, IW, CB>(
             m, n, alpha, A, lda, x, beta, y, incy, row0, rg, cw, lane, part, ring);
     } else if (b < b_full + b_half) {
         const std::int64_t row0 =
             b_full * RG * ROWS + ((b - b_full) * RG + rg) * HALF;
-        gemv_row_group<St, Ar, HALF, ROWS, UNROLL, COLW, PIPE, IW>(
+        gemv_row_group<St, Ar, HALF, ROWS, UNROLL, COLW, PIPE, IW, CB>(
             m, n, alpha, A, lda, x, beta, y, incy, row0, rg, cw, lane, part, ring);
     } else {
         const std::int64_t row0 = b_full * RG * ROWS + b_half * RG * HALF +
                                   ((b - b_full - b_half) * RG + rg) * QUARTER;
-        gemv_row_group<St, Ar, QUARTER, ROWS, UNROLL, COLW, PIPE, IW>(
+        gemv_row_group<St, Ar, QUARTER, ROWS, UNROLL, COLW, PIPE, IW, CB>(
             m, n, alpha, A, lda, x, beta, y, incy, row0, rg, cw, lane, part, ring);
     }
     if (trace != nullptr && threadIdx.x == 0) {
@@ -1021,12 +1045,14 @@ __global__ __launch_bounds__(BLOCK) void gemv_generic_kernel(
 }
 
 template <typename St, typename Ar, int ROWS, int UNROLL, int RG, int COLW,
-          int MINB = (ROWS * UNROLL <= 8) ? 3 : 1, int PIPE = 0, int IW = 2>
+          int MINB = (ROWS * UNROLL <= 8) ? 3 : 1, int PIPE = 0, int IW = 2,
+          int CB = 16>
 int launch_stream(Handle* h, std::int64_t m, std::int64_t n, Ar alpha,
                   const St* A, std::int64_t lda, const St* x, Ar beta, St* y,
                   std::int64_t incy, cudaStream_t stream)
 {
-    auto kernel = gemv_stream_kernel<St, Ar, ROWS, UNROLL, RG, COLW, MINB, PIPE, IW>;
+    auto kernel =
+        gemv_stream_kernel<St, Ar, ROWS, UNROLL, RG, COLW, MINB, PIPE, IW, CB>;
     constexpr size_t smem =
         PIPE >= 2 ? size_t{RG} * COLW * PIPE * (ROWS + 1) * 512 : 0;
     static int resident_on[64] = {};  // CTAs per SM, per instantiation and device
@@ -1207,6 +1233,22 @@ int launch_gemv(Handle* h, std::int64_t m, std::int64_t n, double alpha_d,
         default:
             return launch_variant<St, Ar, 2>(h, variant, m, n, alpha, A, lda, x,
                                              beta, y, incy, stream);
+        }
+    }
+    if (incx == 1) {
+        // 8- or 4-byte aligned operands: the cp.async ring with smaller pieces
+        const std::uintptr_t bits =
+            reinterpret_cast<std::uintptr_t>(A) |
+            reinterpret_cast<std::uintptr_t>(x) |
+            static_cast<std::uintptr_t>(static_cast<std::uint64_t>(lda) *
+                                        sizeof(St));
+        if ((bits & 7u) == 0) {
+            return launch_stream<St, Ar, 4, 2, 1, 8, 3, 3, 2, 8>(
+                h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+        }
+        if ((bits & 3u) == 0) {
+            return launch_stream<St, Ar, 4, 2, 1, 8, 3, 3, 2, 4>(
+                h, m, n, alpha, A, lda, x, beta, y, incy, stream);
         }
     }
     constexpr int BLOCK = 256;

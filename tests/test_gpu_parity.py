@@ -139,6 +139,42 @@ def test_gemv_parity(oracle, handle, ar, st, m, n, lda):
     assert err <= 1.5 * ref_err + 1e-16, (err, ref_err)
 
 
+@pytest.mark.parametrize("ar", AR)
+@pytest.mark.parametrize("st", ST)
+@pytest.mark.parametrize("lda_pad,base_off", [(0, 0), (4, 0), (2, 0), (1, 0), (6, 2), (0, 4), (0, 1),
+                                              (8, 8)])
+def test_gemv_alignment_classes(oracle, handle, ar, st, lda_pad, base_off):
+    """Rows that are only 8-, 4- (or element-) aligned take the cp.async path
+    with smaller pieces (or the scalar kernel): same answers as the 16-byte
+    aligned layout of the same numbers -- bit-identical for fp64 arithmetic
+    (same chunk ownership and accumulators), within tolerance for fp32.  Sizes
+    include several full chunks per warp, a ragged tail and the stride of the
+    reference driver's default sweep (24500)."""
+    for m, n in ((37, 12401), (5, 24500)):
+        lda = n + lda_pad
+        lda_ref = (n + 7) // 8 * 8
+        vals = stored(oracle, m * n, st, first=7)
+        x = stored(oracle, n + 8, st, first=10 ** 7)
+        y = stored(oracle, m, st, first=2 * 10 ** 7)
+        A_ref = np.zeros(m * lda_ref, dtype=NP[st])
+        A_ref.reshape(m, lda_ref)[:, :n] = vals.reshape(m, n)
+        A = np.zeros(base_off + m * lda, dtype=NP[st])
+        A[base_off:].reshape(m, lda)[:, :n] = vals.reshape(m, n)
+        want = run_gemv(handle, ar, A_ref, m, n, lda_ref, x[:n].copy(), 1.0, 1.0, y)
+        yd = dev(y)
+        xo = base_off % 8
+        handle.gemv(ar, m, n, 1.0, dev(A)[base_off:], lda, dev(x)[xo:], 1, 1.0, yd, 1)
+        got = host(yd)
+        x_used = x[xo:xo + n].copy()
+        if xo:
+            want = run_gemv(handle, ar, A_ref, m, n, lda_ref, x_used, 1.0, 1.0, y)
+        if ar == torch.float64:
+            assert np.array_equal(got, want), (m, n, lda, base_off)
+        exact = oracle.exact_gemv(A_ref, m, n, lda_ref, x_used, 1.0, 1.0, y)
+        err = oracle.l1_rel_error(exact, got)
+        assert err <= GEMV_TOL[(ar, st)] * max(1.0, np.sqrt(n / 16384)), (err, lda, base_off)
+
+
 @pytest.mark.parametrize("st", ST)
 def test_gemv_alpha_beta_strides_alignment(oracle, handle, st):
     m, n, lda, incx, incy = 257, 1031, 1040, 3, 2
