@@ -200,11 +200,22 @@ __device__ __forceinline__ __half zero_st<__half>()
 }
 
 // four consecutive elements; `valid` of them are inside the matrix
+// VECTOR: rows are at least 8-byte aligned; `wide` (uniform over the launch):
+// they are 16-byte aligned, so quads wider than 8 bytes use 128-bit loads
 template <typename St, bool VECTOR>
-__device__ __forceinline__ Quad<St> load_quad(const St* p, int valid)
+__device__ __forceinline__ Quad<St> load_quad(const St* p, int valid,
+                                              bool wide = true)
 {
     Quad<St> q;
-    if (VECTOR && valid == kEPL) {
+    if (VECTOR && valid == kEPL && !wide && sizeof(St) > 2) {
+        // 8-byte aligned rows (odd lda of fp64, lda = 2 mod 4 of fp32, ...)
+#pragma unroll
+        for (int i = 0; i < Quad<St>::kWords / 2; ++i) {
+            const uint2 a = ldg_stream_64(reinterpret_cast<const char*>(p) + 8 * i);
+            q.w[2 * i] = a.x;
+            q.w[2 * i + 1] = a.y;
+        }
+    } else if (VECTOR && valid == kEPL) {
         if (sizeof(St) == 8) {
             const uint4 a = ldg_stream_128(p);
             const uint4 b = ldg_stream_128(p + 2);
@@ -300,9 +311,10 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     std::int64_t n, const St* __restrict__ A, std::int64_t lda,
     St* __restrict__ x, std::int64_t incx, Ar* xs,
     unsigned* __restrict__ ticket, long long* __restrict__ trace_arg,
-    int l2_ahead, int whole_block_spin)
+    int l2_ahead, int whole_block_spin, int wide_rows)
 {
     long long* const trace = TRACE ? trace_arg : nullptr;
+    const bool wide = wide_rows != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ar* D = reinterpret_cast<Ar*>(smem_raw);  // kB x kLD
     Ar* xcol = D + kB * kLD;                  // 2 x kB, staged x blocks
@@ -349,7 +361,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
             const int valid =
                 (r < bs) ? (left >= kEPL ? kEPL : (left > 0 ? left : 0)) : 0;
             const std::int64_t rr = (r < bs) ? r0 + r : r0;
-            q[it] = load_quad<St, VECTOR>(A + rr * lda + r0 + c, valid);
+            q[it] = load_quad<St, VECTOR>(A + rr * lda + r0 + c, valid, wide);
         }
 #pragma unroll
         for (int it = 0; it < kIters; ++it) {
@@ -470,7 +482,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                     dst[i].w[w] = 0u;
                 }
             } else {
-                dst[i] = load_quad<St, VECTOR>(row_ptr + c0 + 16 * i, valid);
+                dst[i] = load_quad<St, VECTOR>(row_ptr + c0 + 16 * i, valid, wide);
             }
         }
     };
@@ -918,7 +930,7 @@ template <typename St, typename Ar, bool UPPER, bool UNIT, bool VECTOR,
           bool TRACE = false>
 int launch_one(std::int64_t n, const St* A, std::int64_t lda, St* x,
                std::int64_t incx, Ar* xs, unsigned* ticket, long long* trace,
-               cudaStream_t stream)
+               cudaStream_t stream, bool wide = true)
 {
     auto kernel = trsv_kernel<St, Ar, UPPER, UNIT, VECTOR, TRACE>;
     const size_t smem = sizeof(Ar) * (kB * kLD + 6 * kB);
@@ -937,7 +949,7 @@ int launch_one(std::int64_t n, const St* A, std::int64_t lda, St* x,
     const std::int64_t nb = (n + kB - 1) / kB;
     kernel<<<static_cast<unsigned>(nb), kThreads, smem, stream>>>(
         n, A, lda, x, incx, xs, ticket, trace, tuning().trsv_l2_ahead,
-        tuning().trsv_whole_block_spin);
+        tuning().trsv_whole_block_spin, wide ? 1 : 0);
     ACCBLAS_CUDA(cudaGetLastError());
     return ACCBLAS_OK;
 }
@@ -974,9 +986,13 @@ int launch_trsv(Handle* h, int uplo, int diag, std::int64_t n, const void* A_v,
     Ar* xs = static_cast<Ar*>(trsv_region(h));
     unsigned* ticket = control_words(h) + kCtlTrsvTicket;
 
-    const bool vec =
-        reinterpret_cast<std::uintptr_t>(A) % 16 == 0 &&
-        (static_cast<std::uint64_t>(lda) * sizeof(St)) % 16 == 0;
+    // vector loads need 8-byte aligned rows; 16-byte aligned rows additionally
+    // let fp32 / fp64 quads use 128-bit loads (an fp16 quad is 8 bytes)
+    const std::uintptr_t align_bits =
+        reinterpret_cast<std::uintptr_t>(A) |
+        static_cast<std::uintptr_t>(static_cast<std::uint64_t>(lda) * sizeof(St));
+    const bool vec = (align_bits & 7u) == 0;
+    const bool wide = (align_bits & 15u) == 0;
     const bool upper = uplo == ACCBLAS_UPPER;
     const bool unit = diag == ACCBLAS_UNIT;
     if (trace != nullptr) {
@@ -986,12 +1002,12 @@ int launch_trsv(Handle* h, int uplo, int diag, std::int64_t n, const void* A_v,
             return ACCBLAS_ERR_UNSUPPORTED;
         }
         return launch_one<St, Ar, false, true, true, true>(
-            n, A, lda, x, incx, xs, ticket, trace, stream);
+            n, A, lda, x, incx, xs, ticket, trace, stream, wide);
     }
 #define ACCBLAS_TRSV_CASE(U, N, V)                                          \
     if (upper == U && unit == N && vec == V) {                              \
         return launch_one<St, Ar, U, N, V>(n, A, lda, x, incx, xs, ticket,  \
-                                           trace, stream);                  \
+                                           trace, stream, wide);            \
     }
     ACCBLAS_TRSV_CASE(false, false, false)
     ACCBLAS_TRSV_CASE(false, false, true)

@@ -329,6 +329,26 @@ def test_trsv_parity(oracle, ab, handle, ar, st, n, upper, unit, transpose):
         assert err <= TRSV_TOL[(ar, st)] * max(1.0, n / 300), (err, ref_err)
 
 
+@pytest.mark.parametrize("st", ST)
+@pytest.mark.parametrize("pad", [0, 1, 2, 4, 8])
+def test_trsv_row_alignment_classes(oracle, ab, handle, st, pad):
+    """Rows aligned to 16 bytes (128-bit loads), to 8 bytes (64-bit loads) or
+    less (scalar loads) must give bit-identical solutions of the same system."""
+    n = 700
+    LU = lu_fixture(n, seed=3, lda=n).reshape(n, n)
+    b = stored(oracle, n, st, seed=14)
+    outs = []
+    for lda in (n + 8 - n % 8 + 8, n + pad):
+        M = np.zeros((n, lda))
+        M[:, :n] = LU
+        A = oracle.convert(M.reshape(-1), NP[st])
+        xd = dev(b)
+        handle.trsv(torch.float64, ab.LOWER, ab.UNIT, n, dev(A), lda, xd, 1)
+        torch.cuda.synchronize()
+        outs.append(host(xd))
+    assert np.array_equal(outs[0], outs[1], equal_nan=True), (st, pad)
+
+
 @pytest.mark.parametrize("whole,group", [(1, 1024), (0, 1024), (1, 0), (0, 0), (1, 4096)])
 def test_trsv_wait_modes_give_identical_results(oracle, ab, handle, whole, group):
     """How a caught-up CTA waits for x (whole block / 32 entries at a time) and
