@@ -180,8 +180,12 @@ template <typename St, typename Ar, int BLOCK, int UNROLL>
 __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     const St* __restrict__ x, const St* __restrict__ y, std::int64_t n,
     Ar* __restrict__ partials, unsigned* __restrict__ counter,
-    void* __restrict__ result, int res_dtype, const PeerExchange px, int pdl)
+    void* __restrict__ result, int res_dtype, const PeerExchange px, int pdl,
+    int head)
 {
+    // x and y point at the first 16-byte aligned element; `head` (< 16 /
+    // sizeof(St)) elements in front of it belong to the operands as well
+    // (both vectors misaligned by the same amount, e.g. x[1:] . y[1:])
     constexpr int VEC = vec_traits<St>::elems;
     constexpr std::int64_t TILE = std::int64_t{BLOCK} * VEC * UNROLL;
     __shared__ Ar scratch[kWarp];
@@ -246,6 +250,10 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
 
     // ragged tail (< TILE elements), spread over the whole grid
     Ar tail = Ar{};
+    if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < head) {
+        const std::int64_t i = static_cast<std::int64_t>(threadIdx.x) - head;
+        tail = pair_fma<Ar, St>::apply(x[i], y[i], tail);
+    }
     for (std::int64_t i = num_tiles * TILE +
                           std::int64_t{blockIdx.x} * BLOCK + threadIdx.x;
          i < n; i += std::int64_t{gridDim.x} * BLOCK) {
@@ -305,7 +313,7 @@ __global__ __launch_bounds__(BLOCK) void dot_strided_kernel(
 template <typename St, typename Ar, int BLOCK, int UNROLL>
 int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
                   void* result, int res, int ctas_per_sm, cudaStream_t stream,
-                  const PeerExchange& px)
+                  const PeerExchange& px, int head)
 {
     constexpr int VEC = vec_traits<St>::elems;
     constexpr std::int64_t TILE = std::int64_t{BLOCK} * VEC * UNROLL;
@@ -348,7 +356,7 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
     ACCBLAS_CUDA(cudaLaunchKernelEx(
         &cfg, kernel, static_cast<const St*>(x), static_cast<const St*>(y), n,
         static_cast<Ar*>(payload(h)), control_words(h) + kCtlDotCounter, result,
-        res, px, pdl));
+        res, px, pdl, head));
     return ACCBLAS_OK;
 }
 
@@ -357,22 +365,37 @@ int launch_dot(Handle* h, std::int64_t n, const void* x, std::int64_t incx,
                const void* y, std::int64_t incy, void* result, int res,
                cudaStream_t stream, const PeerExchange& px)
 {
-    const bool aligned =
-        ((reinterpret_cast<std::uintptr_t>(x) |
-          reinterpret_cast<std::uintptr_t>(y)) & 15u) == 0;
+    // contiguous operands with the SAME misalignment: peel the elements in
+    // front of the first 16-byte boundary, stream the rest
+    const std::uintptr_t xa = reinterpret_cast<std::uintptr_t>(x);
+    const std::uintptr_t ya = reinterpret_cast<std::uintptr_t>(y);
+    int head = 0;
+    bool aligned = ((xa | ya) & 15u) == 0;
+    if (!aligned && incx == 1 && incy == 1 && (xa & 15u) == (ya & 15u) &&
+        (xa % sizeof(St)) == 0) {
+        head = static_cast<int>((16u - (xa & 15u)) / sizeof(St));
+        if (head <= n) {
+            aligned = true;
+            x = static_cast<const St*>(x) + head;
+            y = static_cast<const St*>(y) + head;
+            n -= head;
+        } else {
+            head = 0;
+        }
+    }
     if (incx == 1 && incy == 1 && aligned) {
         const int unroll = tuning().dot_unroll;
         const int cps = tuning().dot_ctas_per_sm;
         switch (unroll) {
         case 2:
             return launch_stream<St, Ar, 256, 2>(h, n, x, y, result, res, cps,
-                                                 stream, px);
+                                                 stream, px, head);
         case 8:
             return launch_stream<St, Ar, 256, 8>(h, n, x, y, result, res, cps,
-                                                 stream, px);
+                                                 stream, px, head);
         default:
             return launch_stream<St, Ar, 256, 4>(h, n, x, y, result, res, cps,
-                                                 stream, px);
+                                                 stream, px, head);
         }
     }
     constexpr int BLOCK = 256;

@@ -245,6 +245,31 @@ def test_dot_parity_and_determinism(oracle, handle, ar, st, n):
         assert abs(got - exact) <= 2.0 * abs(float(ref) - exact) + DOT_TOL[ar] * scale * 0.05
 
 
+@pytest.mark.parametrize("ar", AR)
+@pytest.mark.parametrize("st", ST)
+@pytest.mark.parametrize("off", [1, 3, 5])
+def test_dot_common_misalignment_is_peeled(oracle, handle, ar, st, off):
+    """x[off:] . y[off:] (both operands misaligned by the same amount) runs the
+    streaming kernel on the aligned body plus `head` scalar products; different
+    misalignments fall back to the strided kernel.  Both must agree with the
+    oracle."""
+    n = 300_007
+    x = stored(oracle, n + 16, st, seed=31)
+    y = stored(oracle, n + 16, st, seed=32)
+    for ox, oy in ((off, off), (off, off + 1), (0, off)):
+        xs, ys = x[ox:ox + n].copy(), y[oy:oy + n].copy()
+        res = torch.zeros(1, dtype=ar, device=DEV)
+        handle.dot(ar, n, dev(x)[ox:], 1, dev(y)[oy:], 1, res)
+        exact = oracle.exact_dot(xs, ys)
+        scale = float(np.abs(xs.astype(np.float64) * ys.astype(np.float64)).sum())
+        assert abs(float(res.item()) - exact) <= DOT_TOL[ar] * scale, (ox, oy)
+    for tiny in (0, 1, 2, 7):       # shorter than the head
+        res = torch.full((1,), -1.0, dtype=ar, device=DEV)
+        handle.dot(ar, tiny, dev(x)[off:], 1, dev(y)[off:], 1, res)
+        want = float(np.dot(x[off:off + tiny].astype(np.float64), y[off:off + tiny].astype(np.float64)))
+        assert abs(float(res.item()) - want) <= 1e-6 * max(1.0, abs(want))
+
+
 @pytest.mark.parametrize("st", ST)
 def test_dot_result_types_strides_alignment(oracle, handle, st):
     n, incx, incy = 70_001, 2, 3
