@@ -747,6 +747,8 @@ int accblas_tune(const char* key, int value)
         t.gemv_taper = value;
     } else if (!strcmp(key, "dot_pdl")) {
         t.dot_pdl = value;
+    } else if (!strcmp(key, "gemv_force_pieces")) {
+        t.gemv_force_pieces = value;
     } else if (!strcmp(key, "gemv_pdl")) {
         t.gemv_pdl = value;
     } else if (!strcmp(key, "gemv_pipe")) {

@@ -223,6 +223,42 @@ __device__ __forceinline__ double half_bits_to_double(unsigned short bits)
     return d;
 }
 
+// 16 bytes as 64- or 32-bit loads (volatile asm: keeps its place among the
+// other streaming loads); STREAM = do not allocate in L1
+template <int CB, bool STREAM>
+__device__ __forceinline__ uint4 ldg_pieces(const void* p)
+{
+    const char* c = static_cast<const char*>(p);
+    uint4 r;
+    if constexpr (CB == 8) {
+        if constexpr (STREAM) {
+            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(r.x), "=r"(r.y) : "l"(c));
+            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(r.z), "=r"(r.w) : "l"(c + 8));
+        } else {
+            asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(r.x), "=r"(r.y) : "l"(c));
+            asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(r.z), "=r"(r.w) : "l"(c + 8));
+        }
+    } else {
+        unsigned w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (STREAM) {
+                asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];"
+                             : "=r"(w[i]) : "l"(c + 4 * i));
+            } else {
+                asm volatile("ld.global.nc.u32 %0, [%1];"
+                             : "=r"(w[i]) : "l"(c + 4 * i));
+            }
+        }
+        r = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return r;
+}
+
 // One "batch" = one 128-bit vector per lane from each of the ROWS rows plus the
 // matching vector of x: 32 * VEC consecutive columns.  The streaming loop keeps
 // one batch in flight while the previous one is being consumed (software
@@ -230,7 +266,7 @@ __device__ __forceinline__ double half_bits_to_double(unsigned short bits)
 // the matrix stream outstanding -- also while it converts and multiplies.
 // ncu on the unpipelined loop: "long scoreboard" was 4.8 of every 7.9 stall
 // cycles of Acc<fp64,fp16>, issue slots 56 % busy, DRAM 66 %.
-template <typename Ar, typename St, int ROWS, bool FAST, int IW>
+template <typename Ar, typename St, int ROWS, bool FAST, int IW, int CB = 16>
 struct BatchOps {
     static constexpr int VEC = vec_traits<St>::elems;
     static constexpr int COLS = kWarp * VEC;
@@ -268,10 +304,20 @@ struct BatchOps {
                                                 const St* __restrict__ x,
                                                 std::int64_t col, Batch& b)
     {
-        b.x = ldg_cached_128_ordered(x + col);
+        if constexpr (CB == 16) {
+            b.x = ldg_cached_128_ordered(x + col);
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            b.a[r] = ldg_stream_128(row[r] + col);
+            for (int r = 0; r < ROWS; ++r) {
+                b.a[r] = ldg_stream_128(row[r] + col);
+            }
+        } else {
+            // operands that are only 8- / 4-byte aligned: the same 16 bytes
+            // in 64- / 32-bit pieces
+            b.x = ldg_pieces<CB, false>(x + col);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                b.a[r] = ldg_pieces<CB, true>(row[r] + col);
+            }
         }
     }
 
@@ -378,7 +424,7 @@ struct BatchOps {
 template <typename Ar, typename St, int ROWS, bool FAST, int IW, int STAGES,
           int CB = 16>
 struct AsyncOps {
-    using B = BatchOps<Ar, St, ROWS, FAST, IW>;
+    using B = BatchOps<Ar, St, ROWS, FAST, IW, CB>;
     static constexpr int VEC = B::VEC;
     static constexpr int COLS = B::COLS;
     static constexpr unsigned STAGE_BYTES = (ROWS + 1) * 512;
@@ -548,7 +594,7 @@ __device__ __forceinline__ void gemv_row_group(
         } else if constexpr (PIPE == 1 && UNROLL == 2) {
             // same chunk ownership and the same accumulator per (row, vector
             // slot) as the unpipelined loop: results are bit-identical
-            BatchOps<Ar, St, R, FAST, IW>::template stream<COLW>(
+            BatchOps<Ar, St, R, FAST, IW, CB>::template stream<COLW>(
                 row, x, full_chunks, cw, lane, part_acc, chk);
         } else {
             for (std::int64_t k = cw; k < full_chunks; k += COLW) {
@@ -1211,6 +1257,23 @@ int launch_gemv(Handle* h, std::int64_t m, std::int64_t n, double alpha_d,
         ((reinterpret_cast<std::uintptr_t>(A) |
           reinterpret_cast<std::uintptr_t>(x)) & 15u) == 0 &&
         (static_cast<std::uint64_t>(lda) * sizeof(St)) % 16 == 0;
+    {
+        // Acc<fp64,fp16>: the register pipeline fed by 64-bit loads (finer
+        // grained: half a vector per request) beats the 128-bit one by 5 % on
+        // aligned data too (same box: 5826 -> 6100-6170 GB/s); every other
+        // pair is 2-8 % faster with 128-bit loads.  gemv_force_pieces: 8 = all
+        // pairs through the 64-bit pipeline, -1 = none (for A/B runs).
+        const Tuning& t = tuning();
+        const bool fast_default =
+            use_scaled_half<Ar, St>::value && t.gemv_force_pieces == 0 &&
+            t.gemv_pipe < 0 && t.gemv_variant == 0 && t.gemv_unroll == 2 &&
+            t.gemv_stages == 0 && t.gemv_intwords == 2 &&
+            m >= std::int64_t{4} * 8 * h->sm_count;
+        if (vec_ok && (t.gemv_force_pieces == 8 || fast_default)) {
+            return launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 2, 8>(
+                h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+        }
+    }
     if (vec_ok) {
         int variant = tuning().gemv_variant;
         int unroll = tuning().gemv_unroll;
@@ -1242,13 +1305,18 @@ int launch_gemv(Handle* h, std::int64_t m, std::int64_t n, double alpha_d,
             reinterpret_cast<std::uintptr_t>(x) |
             static_cast<std::uintptr_t>(static_cast<std::uint64_t>(lda) *
                                         sizeof(St));
+        const bool ring = tuning().gemv_pipe >= 2;
         if ((bits & 7u) == 0) {
-            return launch_stream<St, Ar, 4, 2, 1, 8, 3, 3, 2, 8>(
-                h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+            return ring ? launch_stream<St, Ar, 4, 2, 1, 8, 3, 3, 2, 8>(
+                              h, m, n, alpha, A, lda, x, beta, y, incy, stream)
+                        : launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 2, 8>(
+                              h, m, n, alpha, A, lda, x, beta, y, incy, stream);
         }
         if ((bits & 3u) == 0) {
-            return launch_stream<St, Ar, 4, 2, 1, 8, 3, 3, 2, 4>(
-                h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+            return ring ? launch_stream<St, Ar, 4, 2, 1, 8, 3, 3, 2, 4>(
+                              h, m, n, alpha, A, lda, x, beta, y, incy, stream)
+                        : launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 2, 4>(
+                              h, m, n, alpha, A, lda, x, beta, y, incy, stream);
         }
     }
     constexpr int BLOCK = 256;

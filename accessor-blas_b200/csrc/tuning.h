@@ -15,6 +15,7 @@ struct Tuning {
     int gemv_pipe = -1;        // default GEMV shape: -1 = per pair, 0 = plain loop, 1 = register pipeline, 3 / 4 = cp.async ring depth
     int gemv_intwords = 2;     // Acc<fp64,fp16>: words per 128-bit vector widened on the integer pipes (rest: F2F)
     int gemv_pdl = 1;          // programmatic dependent launch: back-to-back GEMVs overlap tail and ramp
+    int gemv_force_pieces = 0; // 16-byte aligned operands through the 64-bit-load pipeline: 0 = Acc<fp64,fp16> only, 8 = all pairs, -1 = none
     int gemv_taper = 1;        // shorter row groups at the end of the grid
     int gemv_stages = 0;       // 0 = register path, 2..4 = bulk-copy ring depth
     int trsv_whole_block_spin = 1;  // TRSV: a caught-up CTA waits for a whole x block (1) or 32 entries at a time (0)

@@ -180,6 +180,50 @@ if "b2b" in which:
         del x, y
     ab.tune("dot_pdl", 1)
 
+if "misaligned" in which:
+    # rows that are only 8-byte aligned (the reference driver's stride 24500 for
+    # fp16; 16384 + 4 here): register pipeline with 64-bit loads vs cp.async ring
+    m = k = 16384
+    for st, pad in ((torch.float16, 4), (torch.float32, 2), (torch.float64, 1)):
+        lda = k + pad
+        A = torch.empty(m * lda, dtype=st, device=dev)
+        x = torch.empty(k, dtype=st, device=dev)
+        y = torch.zeros(m, dtype=st, device=dev)
+        h.fill_uniform(m, lda, A, lda, 42, 0)
+        h.fill_uniform(k, 1, x, 1, 42, m * lda)
+        for ar in (torch.float64, torch.float32):
+            for pipe in (1, 3, 1, 3):
+                ab.tune("gemv_pipe", pipe)
+                ms = min_of_10(lambda: h.gemv(ar, m, k, 1.0, A, lda, x, 1, 0.0, y, 1), torch)
+                gbs = gemv_bytes(m, k, A.element_size()) / ms / 1e6
+                key = f"gemv lda={lda} Acc<{NAME[ar]},{NAME[st]}> pipe={pipe}"
+                while key in results:
+                    key += " (repeat)"
+                results[key] = round(gbs, 1)
+                print(key, f"{gbs:8.1f} GB/s", flush=True)
+        del A
+    ab.tune("gemv_pipe", -1)
+    # aligned data: default path vs the 64-bit-load pipeline
+    m = k = 16384
+    for st in (torch.float16, torch.float32, torch.float64):
+        A = torch.empty(m * k, dtype=st, device=dev)
+        x = torch.empty(k, dtype=st, device=dev)
+        y = torch.zeros(m, dtype=st, device=dev)
+        h.fill_uniform(m, k, A, k, 42, 0)
+        h.fill_uniform(k, 1, x, 1, 42, m * k)
+        for ar in (torch.float64, torch.float32):
+            for force in (-1, 8, -1, 8):
+                ab.tune("gemv_force_pieces", force)
+                ms = min_of_10(lambda: h.gemv(ar, m, k, 1.0, A, k, x, 1, 0.0, y, 1), torch)
+                gbs = gemv_bytes(m, k, A.element_size()) / ms / 1e6
+                key = f"gemv aligned Acc<{NAME[ar]},{NAME[st]}> force_pieces={force}"
+                while key in results:
+                    key += " (repeat)"
+                results[key] = round(gbs, 1)
+                print(key, f"{gbs:8.1f} GB/s", flush=True)
+        del A
+    ab.tune("gemv_force_pieces", 0)
+
 out = ROOT / "gpurun_out"
 out.mkdir(exist_ok=True)
 (out / "tune.json").write_text(json.dumps(results, indent=1))
