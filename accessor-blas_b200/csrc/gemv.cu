@@ -1238,6 +1238,20 @@ int launch_variant(Handle* h, int variant, std::int64_t m, std::int64_t n,
                                                   beta, y, incy, stream);
 }
 
+// x with a stride: packed once into the workspace (n elements, a few
+// microseconds at most), so that the matrix stream -- m times larger -- keeps
+// its vector path
+template <typename St>
+__global__ __launch_bounds__(256) void gather_strided_kernel(
+    const St* __restrict__ x, std::int64_t incx, St* __restrict__ out,
+    std::int64_t n)
+{
+    const std::int64_t i = std::int64_t{blockIdx.x} * 256 + threadIdx.x;
+    if (i < n) {
+        out[i] = x[i * incx];
+    }
+}
+
 template <typename St, typename Ar>
 int launch_gemv(Handle* h, std::int64_t m, std::int64_t n, double alpha_d,
                 const void* A_v, std::int64_t lda, const void* x_v,
@@ -1251,6 +1265,23 @@ int launch_gemv(Handle* h, std::int64_t m, std::int64_t n, double alpha_d,
     St* y = static_cast<St*>(y_v);
     if (m == 0) {
         return ACCBLAS_OK;
+    }
+    if (incx != 1 && n > 0) {
+        const size_t bytes = static_cast<size_t>(n) * sizeof(St);
+        int rc = ensure_workspace(h, kScratchBytes + bytes, stream);
+        if (rc != ACCBLAS_OK) {
+            return rc;
+        }
+        // the region doubles as the TRSV progress vector: it has to be armed
+        // again before the next solve
+        h->trsv_armed_bytes = 0;
+        St* packed = static_cast<St*>(trsv_region(h));
+        gather_strided_kernel<St>
+            <<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+                x, incx, packed, n);
+        ACCBLAS_CUDA(cudaGetLastError());
+        x = packed;
+        incx = 1;
     }
     const bool vec_ok =
         incx == 1 &&

@@ -406,6 +406,29 @@ def test_trsv_wait_modes_give_identical_results(oracle, ab, handle, whole, group
         ab.tune("trsv_l2_ahead", 1024)
 
 
+def test_strided_gemv_then_trsv_share_the_workspace(oracle, ab, handle):
+    """GEMV packs a strided x into the region TRSV uses as its progress vector;
+    the next solve must find it armed again."""
+    n, lda = 900, 904
+    LU = lu_fixture(n, seed=41, lda=lda)
+    A = oracle.convert(LU, np.float32)
+    b = stored(oracle, n, torch.float32, seed=15)
+    exact = oracle.exact_trsv(A, n, lda, b, False, True)
+    Ad = dev(A)
+    for _ in range(2):
+        m, k, incx = 64, 5000, 3
+        G = stored(oracle, m * k, torch.float32, first=123)
+        xg = stored(oracle, k * incx, torch.float32, first=10 ** 6)
+        yg = np.zeros(m, dtype=np.float32)
+        got = run_gemv(handle, torch.float64, G, m, k, k, xg, 1.0, 0.0, yg, incx=incx)
+        ex = oracle.exact_gemv(G, m, k, k, xg, 1.0, 0.0, yg, incx, 1)
+        assert oracle.l1_rel_error(ex, got) <= GEMV_TOL[(torch.float64, torch.float32)]
+        xd = dev(b)
+        handle.trsv(torch.float64, ab.LOWER, ab.UNIT, n, Ad, lda, xd, 1)
+        torch.cuda.synchronize()
+        assert oracle.l1_rel_error(exact, host(xd)) < 2e-6 * max(1, n / 300)
+
+
 def test_trsv_repeated_calls_and_strided_x(oracle, ab, handle):
     n, lda, incx = 700, 704, 2
     LU = lu_fixture(n, seed=5, lda=lda)
