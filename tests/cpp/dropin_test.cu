@@ -11,6 +11,8 @@
 #include <random>
 #include <vector>
 
+#include <accessor/row_major.hpp>
+
 #include <accblas/dot_kernels.cuh>
 #include <accblas/gemv_kernels.cuh>
 #include <accblas/trsv_kernels.cuh>
@@ -132,6 +134,23 @@ int main()
         synchronize();
         const double e4 = l1_rel(want_f, widen(to_host(fy, m)));
         check(e4 < 6e-8, "acc_gemv(range...)", e4, 0);
+        // "all other accessors work accordingly" (README.md:19): the same
+        // kernel template over the plain row_major accessor (fp64 in, fp64 out)
+        {
+            CUDA_CALL(cudaMemcpy(dy, y.data(), sizeof(double) * m,
+                                 cudaMemcpyHostToDevice));
+            using rm = gko::acc::row_major<double, 2>;
+            using rm_range = gko::acc::range<rm>;
+            using rm_crange = gko::acc::range<typename rm::const_accessor>;
+            auto m_rm = rm_crange(m_info.size, static_cast<const double*>(dA), ms);
+            auto x_rm = rm_crange(x_info.size, static_cast<const double*>(dx), xs);
+            auto res_rm = rm_range(res_info.size, dy, rs);
+            kernel::acc_gemv<512><<<static_cast<unsigned>(m), 512>>>(
+                0.5, m_rm, x_rm, 2.0, res_rm);
+            synchronize();
+            const double e6 = l1_rel(want, to_host(dy, m));
+            check(e6 < 1e-14, "kernel::acc_gemv<512> over row_major", e6, 0);
+        }
         // plain kernel template
         CUDA_CALL(cudaMemcpy(dy, y.data(), sizeof(double) * m,
                              cudaMemcpyHostToDevice));
