@@ -11,7 +11,7 @@
 //     line group.  Many small CTAs (thousands) keep the SMs evenly loaded to
 //     the very end of the launch -- measured on B200 the "one warp owns 4
 //     whole rows" shape loses 20 % to the tail, the column-split shape does
-//     not (profiles/r01_tune.md);
+//     not (profiles/r01_summary.md);
 //   * the matching x vectors are loaded once per chunk through L1 (shared by
 //     all CTAs of the SM), converted to the arithmetic type once and reused
 //     for the ROWS rows;
@@ -19,9 +19,18 @@
 //     FMA in the arithmetic type, the row reduction is a warp-shuffle butterfly
 //     plus one shared-memory hop between the COLW warps (fixed order);
 //   * fp16 storage with fp64 arithmetic would be bound by the 64-bit
-//     conversion pipe (F2F.F64.F32 issues at a quarter of the rate the HBM
-//     stream needs), so that pair widens with integer bit-field moves instead
-//     (see HalfToDoubleScaled below); results are bit-identical.
+//     conversion pipe (F2F issues at a quarter of the rate the HBM stream
+//     needs), so that pair widens half of every vector with integer
+//     instructions instead (see HalfToDoubleScaled below) and runs a register
+//     software pipeline fed by 64-bit loads; results are bit-identical;
+//   * operands that are only 8- or 4-byte aligned (odd row strides, sliced
+//     bases) take the same pipeline with 64- / 32-bit loads, a strided x is
+//     packed once: the scalar kernel is left with fp16 rows of odd stride;
+//   * back-to-back calls overlap: programmatic dependent launch lets the next
+//     GEMV's CTAs occupy the SM slots the last wave leaves empty and prefetch
+//     into L2 while they wait for the predecessor to finish.
+// Selectable alternatives that were measured and did not win (tools/tune.py):
+// a TMA bulk-copy ring (gemv_bulk_kernel), a cp.async ring (AsyncOps).
 // The result is rounded once to the storage type on the way out, exactly like
 // the accessor's proxy assignment (cuda/gemv_kernels.cuh:106-111).
 #include "common.cuh"
