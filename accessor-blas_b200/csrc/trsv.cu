@@ -389,7 +389,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     }
     __syncthreads();
     ACCBLAS_TRACE(1, clock64());
-    if (warp < kNSB) {
+    if (warp < kNSB && warp * kSB < bs) {  // padding-only sub-blocks are identity
         invert_subblock<Ar, UPPER, UNIT>(D + (warp * kSB) * kLD + warp * kSB,
                                          inv_diag + warp * kSB, lane);
     }
@@ -415,13 +415,17 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                 const Ar* inv = D + (mg * kSB + i) * kLD + mg * kSB;
                 const Ar* blk = D + (mg * kSB) * kLD + mt * kSB + jp;
                 Ar o0 = Ar{}, o1 = Ar{};
+                // sub-blocks made of padding only (short last block, small
+                // systems) hold zeros already: nothing to multiply
+                if (mg * kSB < bs && mt * kSB < bs) {
 #pragma unroll 8
-                for (int kk = 0; kk < kSB; ++kk) {
-                    const Ar a = inv[kk];
-                    const Pair<Ar> d =
-                        *reinterpret_cast<const Pair<Ar>*>(blk + kk * kLD);
-                    o0 = fma_ar(a, d.a, o0);
-                    o1 = fma_ar(a, d.b, o1);
+                    for (int kk = 0; kk < kSB; ++kk) {
+                        const Ar a = inv[kk];
+                        const Pair<Ar> d =
+                            *reinterpret_cast<const Pair<Ar>*>(blk + kk * kLD);
+                        o0 = fma_ar(a, d.a, o0);
+                        o1 = fma_ar(a, d.b, o1);
+                    }
                 }
                 out[slot][0] = o0;
                 out[slot][1] = o1;
@@ -536,7 +540,8 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     const int grp = UPPER ? kNSB - 1 - mem_sub : mem_sub;  // solve index
 
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
+    // (the first CTA of the solve order has nobody to wait for: no rehearsal)
+    for (int pass = (k == 0 ? 1 : 0); pass < 2; ++pass) {
         const bool real = pass == 1;
         Ar* rhs_cur = real ? rhs : scratch;
         // fp32 arithmetic: one accumulator per quad slot, so a chain is no
