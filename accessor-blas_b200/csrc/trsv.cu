@@ -51,6 +51,18 @@ constexpr int kLD = kB + 8;
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / kWarp;
 constexpr int kEPL = 4;                    // elements per lane per row
+// Widen a panel BEFORE its x block is looked at (the conversions are then off
+// the critical path of a CTA that has caught up with the chain), or let the
+// compiler interleave the conversions with the FMAs.  Forcing the widened
+// panel (64 registers of doubles) to stay live across the barrier costs more
+// than it saves for fp32 storage with fp64 arithmetic: the CTAs are almost
+// always BEHIND the chain (x already there), and the kernel sits at the
+// 128-register limit.  Same box: 415.6 -> 328.7 us without it; the other
+// pairs are within 1-3 % either way and keep it.
+template <typename St, typename Ar>
+struct pre_convert : std::true_type {};
+template <>
+struct pre_convert<float, double> : std::false_type {};
 
 template <typename Ar>
 struct Sentinel;
@@ -200,15 +212,16 @@ __device__ __forceinline__ __half zero_st<__half>()
 }
 
 // four consecutive elements; `valid` of them are inside the matrix
-// VECTOR: rows are at least 8-byte aligned; `wide` (uniform over the launch):
-// they are 16-byte aligned, so quads wider than 8 bytes use 128-bit loads
-template <typename St, bool VECTOR>
-__device__ __forceinline__ Quad<St> load_quad(const St* p, int valid,
-                                              bool wide = true)
+// VW = vector width of the row loads in bytes: 16 (rows 16-byte aligned),
+// 8 (8-byte aligned: odd lda of fp64, lda = 2 mod 4 of fp32; an fp16 quad is
+// 8 bytes anyway) or 0 (scalar loads).  Compile time: a run-time flag in this
+// loop cost fp64 storage 5 %.
+template <typename St, int VW>
+__device__ __forceinline__ Quad<St> load_quad(const St* p, int valid)
 {
+    constexpr bool VECTOR = VW != 0;
     Quad<St> q;
-    if (VECTOR && valid == kEPL && !wide && sizeof(St) > 2) {
-        // 8-byte aligned rows (odd lda of fp64, lda = 2 mod 4 of fp32, ...)
+    if (VW == 8 && valid == kEPL && sizeof(St) > 2) {
 #pragma unroll
         for (int i = 0; i < Quad<St>::kWords / 2; ++i) {
             const uint2 a = ldg_stream_64(reinterpret_cast<const char*>(p) + 8 * i);
@@ -305,16 +318,15 @@ __device__ __forceinline__ void invert_subblock(Ar* T, Ar* inv_diag, int lane)
 // TRACE = false (production): the timeline probes below compile away entirely
 // -- even predicated off they cost registers (this kernel sits at the 128
 // register limit of a 512-thread CTA) and scoreboard waits.
-template <typename St, typename Ar, bool UPPER, bool UNIT, bool VECTOR,
+template <typename St, typename Ar, bool UPPER, bool UNIT, int VW,
           bool TRACE>
 __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     std::int64_t n, const St* __restrict__ A, std::int64_t lda,
     St* __restrict__ x, std::int64_t incx, Ar* xs,
     unsigned* __restrict__ ticket, long long* __restrict__ trace_arg,
-    int l2_ahead, int whole_block_spin, int wide_rows)
+    int l2_ahead, int whole_block_spin)
 {
     long long* const trace = TRACE ? trace_arg : nullptr;
-    const bool wide = wide_rows != 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ar* D = reinterpret_cast<Ar*>(smem_raw);  // kB x kLD
     Ar* xcol = D + kB * kLD;                  // 2 x kB, staged x blocks
@@ -361,7 +373,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
             const int valid =
                 (r < bs) ? (left >= kEPL ? kEPL : (left > 0 ? left : 0)) : 0;
             const std::int64_t rr = (r < bs) ? r0 + r : r0;
-            q[it] = load_quad<St, VECTOR>(A + rr * lda + r0 + c, valid, wide);
+            q[it] = load_quad<St, VW>(A + rr * lda + r0 + c, valid);
         }
 #pragma unroll
         for (int it = 0; it < kIters; ++it) {
@@ -486,7 +498,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                     dst[i].w[w] = 0u;
                 }
             } else {
-                dst[i] = load_quad<St, VECTOR>(row_ptr + c0 + 16 * i, valid, wide);
+                dst[i] = load_quad<St, VW>(row_ptr + c0 + 16 * i, valid);
             }
         }
     };
@@ -648,7 +660,9 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
 #pragma unroll
                     for (int e = 0; e < kEPL; ++e) {
                         cv[i][e] = cur[i].template get<Ar>(e);
-                        pin_register(cv[i][e]);
+                        if (pre_convert<St, Ar>::value) {
+                            pin_register(cv[i][e]);
+                        }
                     }
                 }
                 if (p == 0 && phase_log) {
@@ -931,13 +945,13 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     }
 }
 
-template <typename St, typename Ar, bool UPPER, bool UNIT, bool VECTOR,
+template <typename St, typename Ar, bool UPPER, bool UNIT, int VW,
           bool TRACE = false>
 int launch_one(std::int64_t n, const St* A, std::int64_t lda, St* x,
                std::int64_t incx, Ar* xs, unsigned* ticket, long long* trace,
-               cudaStream_t stream, bool wide = true)
+               cudaStream_t stream)
 {
-    auto kernel = trsv_kernel<St, Ar, UPPER, UNIT, VECTOR, TRACE>;
+    auto kernel = trsv_kernel<St, Ar, UPPER, UNIT, VW, TRACE>;
     const size_t smem = sizeof(Ar) * (kB * kLD + 6 * kB);
     // the opt-in is per device (and per instantiation)
     static bool configured[64] = {};
@@ -954,7 +968,7 @@ int launch_one(std::int64_t n, const St* A, std::int64_t lda, St* x,
     const std::int64_t nb = (n + kB - 1) / kB;
     kernel<<<static_cast<unsigned>(nb), kThreads, smem, stream>>>(
         n, A, lda, x, incx, xs, ticket, trace, tuning().trsv_l2_ahead,
-        tuning().trsv_whole_block_spin, wide ? 1 : 0);
+        tuning().trsv_whole_block_spin);
     ACCBLAS_CUDA(cudaGetLastError());
     return ACCBLAS_OK;
 }
@@ -996,32 +1010,40 @@ int launch_trsv(Handle* h, int uplo, int diag, std::int64_t n, const void* A_v,
     const std::uintptr_t align_bits =
         reinterpret_cast<std::uintptr_t>(A) |
         static_cast<std::uintptr_t>(static_cast<std::uint64_t>(lda) * sizeof(St));
-    const bool vec = (align_bits & 7u) == 0;
-    const bool wide = (align_bits & 15u) == 0;
+    // 16 -> 128-bit loads, 8 -> 64-bit loads, 0 -> scalar; an fp16 quad is 8
+    // bytes, so its 16-byte case is the 8-byte one
+    int vw = (align_bits & 15u) == 0 ? 16 : ((align_bits & 7u) == 0 ? 8 : 0);
+    if (sizeof(St) == 2 && vw == 16) {
+        vw = 8;
+    }
     const bool upper = uplo == ACCBLAS_UPPER;
     const bool unit = diag == ACCBLAS_UNIT;
     if (trace != nullptr) {
         // development timeline (tools/trsv_trace.py): one instantiation only
-        if (upper || !unit || !vec) {
-            set_error("trsv trace: lower / unit / aligned operands only");
+        constexpr int kTraceVw = sizeof(St) == 2 ? 8 : 16;
+        if (upper || !unit || vw != kTraceVw) {
+            set_error("trsv trace: lower / unit / 16-byte aligned operands only");
             return ACCBLAS_ERR_UNSUPPORTED;
         }
-        return launch_one<St, Ar, false, true, true, true>(
-            n, A, lda, x, incx, xs, ticket, trace, stream, wide);
+        return launch_one<St, Ar, false, true, kTraceVw, true>(
+            n, A, lda, x, incx, xs, ticket, trace, stream);
     }
 #define ACCBLAS_TRSV_CASE(U, N, V)                                          \
-    if (upper == U && unit == N && vec == V) {                              \
+    if (upper == U && unit == N && vw == V) {                               \
         return launch_one<St, Ar, U, N, V>(n, A, lda, x, incx, xs, ticket,  \
-                                           trace, stream, wide);            \
+                                           trace, stream);                  \
     }
-    ACCBLAS_TRSV_CASE(false, false, false)
-    ACCBLAS_TRSV_CASE(false, false, true)
-    ACCBLAS_TRSV_CASE(false, true, false)
-    ACCBLAS_TRSV_CASE(false, true, true)
-    ACCBLAS_TRSV_CASE(true, false, false)
-    ACCBLAS_TRSV_CASE(true, false, true)
-    ACCBLAS_TRSV_CASE(true, true, false)
-    ACCBLAS_TRSV_CASE(true, true, true)
+#define ACCBLAS_TRSV_WIDTHS(U, N)                  \
+    ACCBLAS_TRSV_CASE(U, N, 0)                     \
+    ACCBLAS_TRSV_CASE(U, N, 8)                     \
+    if constexpr (sizeof(St) != 2) {               \
+        ACCBLAS_TRSV_CASE(U, N, 16)                \
+    }
+    ACCBLAS_TRSV_WIDTHS(false, false)
+    ACCBLAS_TRSV_WIDTHS(false, true)
+    ACCBLAS_TRSV_WIDTHS(true, false)
+    ACCBLAS_TRSV_WIDTHS(true, true)
+#undef ACCBLAS_TRSV_WIDTHS
 #undef ACCBLAS_TRSV_CASE
     return ACCBLAS_ERR_INVALID;
 }
