@@ -251,7 +251,7 @@ __device__ __forceinline__ uint4 ldg_pieces(const void* p)
             asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];"
                          : "=r"(r.z), "=r"(r.w) : "l"(c + 8));
         }
-    } else {
+    } else if constexpr (CB == 4) {
         unsigned w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -264,6 +264,24 @@ __device__ __forceinline__ uint4 ldg_pieces(const void* p)
             }
         }
         r = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        // 2-byte aligned (fp16 rows with an odd stride): eight 16-bit loads,
+        // all in flight together, instead of the scalar kernel's one per turn
+        unsigned short hw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if constexpr (STREAM) {
+                asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];"
+                             : "=h"(hw[i]) : "l"(c + 2 * i));
+            } else {
+                asm volatile("ld.global.nc.u16 %0, [%1];"
+                             : "=h"(hw[i]) : "l"(c + 2 * i));
+            }
+        }
+        r = make_uint4(hw[0] | (static_cast<unsigned>(hw[1]) << 16),
+                       hw[2] | (static_cast<unsigned>(hw[3]) << 16),
+                       hw[4] | (static_cast<unsigned>(hw[5]) << 16),
+                       hw[6] | (static_cast<unsigned>(hw[7]) << 16));
     }
     return r;
 }
@@ -1357,6 +1375,13 @@ int launch_gemv(Handle* h, std::int64_t m, std::int64_t n, double alpha_d,
                               h, m, n, alpha, A, lda, x, beta, y, incy, stream)
                         : launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 2, 4>(
                               h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+        }
+        if constexpr (sizeof(St) == 2 && sizeof(Ar) == 8) {
+            // fp16 with an odd stride or base (element aligned only), fp64
+            // arithmetic: 2.2 TB/s against 1.35 of the scalar kernel (for
+            // fp32 arithmetic the scalar kernel's 2.4 TB/s stays ahead)
+            return launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 2, 2>(
+                h, m, n, alpha, A, lda, x, beta, y, incy, stream);
         }
     }
     constexpr int BLOCK = 256;
