@@ -1325,9 +1325,18 @@ int launch_gemv(Handle* h, std::int64_t m, std::int64_t n, double alpha_d,
         const bool fast_default =
             use_scaled_half<Ar, St>::value && t.gemv_force_pieces == 0 &&
             t.gemv_pipe < 0 && t.gemv_variant == 0 && t.gemv_unroll == 2 &&
-            t.gemv_stages == 0 && t.gemv_intwords == 2 &&
-            m >= std::int64_t{4} * 8 * h->sm_count;
+            t.gemv_stages == 0 && m >= std::int64_t{4} * 8 * h->sm_count;
         if (vec_ok && (t.gemv_force_pieces == 8 || fast_default)) {
+            if constexpr (use_scaled_half<Ar, St>::value) {
+                if (t.gemv_intwords == 1) {
+                    return launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 1, 8>(
+                        h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+                }
+                if (t.gemv_intwords == 3) {
+                    return launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 3, 8>(
+                        h, m, n, alpha, A, lda, x, beta, y, incy, stream);
+                }
+            }
             return launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 2, 8>(
                 h, m, n, alpha, A, lda, x, beta, y, incy, stream);
         }
