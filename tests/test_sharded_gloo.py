@@ -71,6 +71,33 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
                  1.0, 0.0, want)
     assert np.array_equal(full.numpy(), want)  # no cross-rank reduction: bit-identical
 
+    # --- in-kernel exchange: the set-up handshake (host logic only; the GPU
+    #     side is tests/test_gpu_parity.py + tests/multi_gpu_dot.py) ----------
+    class FakeHandle:
+        def __init__(self, r):
+            self.r, self.connected, self.calls = r, None, 0
+
+        def peer_export(self):
+            return bytes([self.r]) * 64
+
+        def peer_connect_ipc(self, w, r, handles):
+            self.connected = (w, r, handles)
+
+        def dot_allreduce(self, ar, n_, x_, incx, y_, incy, result, stream=None):
+            self.calls += 1
+            result.fill_(float(n_))
+
+    fh = FakeHandle(rank)
+    sd = sharded.ShardedDot(fh, torch.float64, n, fused=True)
+    assert sd.fused
+    w, r, handles = fh.connected
+    assert (w, r) == (world, rank)
+    assert handles == b"".join(bytes([q]) * 64 for q in range(world))  # rank order
+    xl = torch.zeros(sd.count, dtype=torch.float32)
+    out = sd(xl, xl, torch.float32)
+    assert fh.calls == 1 and out.dtype == torch.float32 and out.item() == float(sd.count)
+    assert not sharded.ShardedDot(FakeHandle(rank), torch.float64, n, fused=False).fused
+
     # fp16 vectors travel as raw words
     hv = torch.arange(16, dtype=torch.float16) if rank == 0 else torch.zeros(16, dtype=torch.float16)
     sharded.broadcast_vector(hv)
