@@ -55,6 +55,9 @@ SYMBOLS = {
     "accblas_peer_connect_ptrs": (c_int, [_P, c_int, c_int, POINTER(_P), POINTER(c_int)]),
     "accblas_dot_allreduce": (c_int, [_P, c_int, c_int, c_int, c_int64, _P, c_int64, _P,
                                       c_int64, _P, _P]),
+    "accblas_peer_disconnect": (c_int, [_P]),
+    "accblas_peer_set_timeout": (c_int, [_P, c_double]),
+    "accblas_peer_status": (c_int, [_P, POINTER(c_uint64)]),
 }
 
 BASELINE_SYMBOLS = {

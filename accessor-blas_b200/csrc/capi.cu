@@ -188,6 +188,8 @@ const char* accblas_status_string(int status)
         return "device allocation failure";
     case ACCBLAS_ERR_DATA:
         return "data-dependent failure";
+    case ACCBLAS_ERR_PEER:
+        return "multi-GPU exchange failure";
     default:
         return "unknown status";
     }
@@ -293,6 +295,9 @@ int accblas_destroy(accblas_handle_t handle)
     if (h->mailbox) {
         cudaFree(h->mailbox);
     }
+    if (h->peer_status_host) {
+        cudaFreeHost(h->peer_status_host);
+    }
     delete h;
     return ACCBLAS_OK;
 }
@@ -347,6 +352,15 @@ int accblas_dot(accblas_handle_t handle, accblas_dtype ar, accblas_dtype st,
 }
 
 // ---- multi-GPU DOT: partials combined inside the kernel over peer memory ----
+// Life cycle of the exchange state of a handle:
+//   export / mailbox   allocates the mailbox ZEROED (once); from here on peers
+//                      may map it and publish into it at any time
+//   connect_*          maps the peers; does NOT touch this rank's mailbox, so
+//                      an entry a faster peer has already published survives
+//                      (no barrier is needed between connect and the first
+//                      call); epochs count from 1
+//   disconnect         unmaps the peers and FREES the mailbox: a new group
+//                      starts from a fresh export, never from reused slots
 static int ensure_mailbox(Handle* h)
 {
     if (h->mailbox == nullptr) {
@@ -355,7 +369,31 @@ static int ensure_mailbox(Handle* h)
         ACCBLAS_CUDA(cudaMemset(h->mailbox, 0, accblas::kMailboxBytes));
         ACCBLAS_CUDA(cudaDeviceSynchronize());
     }
+    if (h->peer_status_host == nullptr) {
+        void* host = nullptr;
+        ACCBLAS_CUDA(cudaHostAlloc(&host, sizeof(unsigned long long),
+                                   cudaHostAllocMapped));
+        h->peer_status_host = static_cast<unsigned long long*>(host);
+        *h->peer_status_host = 0ull;
+        void* dev = nullptr;
+        ACCBLAS_CUDA(cudaHostGetDevicePointer(&dev, host, 0));
+        h->peer_status_dev = static_cast<unsigned long long*>(dev);
+    }
     return ACCBLAS_OK;
+}
+
+static void peer_unmap(Handle* h)
+{
+    for (int i = 0; i < accblas::kMaxPeers; ++i) {
+        if (h->peer_mailbox[i] && h->peer_is_ipc[i]) {
+            cudaIpcCloseMemHandle(h->peer_mailbox[i]);
+        }
+        h->peer_mailbox[i] = nullptr;
+        h->peer_is_ipc[i] = false;
+    }
+    h->peer_world = 0;
+    h->peer_rank = 0;
+    h->peer_epoch = 0;
 }
 
 int accblas_peer_mailbox(accblas_handle_t handle, void** device_ptr)
@@ -393,27 +431,24 @@ int accblas_peer_export(accblas_handle_t handle, void* ipc_handle_64_bytes)
     return ACCBLAS_OK;
 }
 
-static int peer_reset(Handle* h, int world, int rank)
+static int peer_begin(Handle* h, int world, int rank)
 {
     if (world < 1 || world > accblas::kMaxPeers || rank < 0 || rank >= world) {
         accblas::set_error("peer connect: world=%d rank=%d (at most %d peers)",
                            world, rank, accblas::kMaxPeers);
         return ACCBLAS_ERR_INVALID;
     }
+    if (h->peer_world != 0) {
+        accblas::set_error(
+            "peer connect: handle already belongs to a group of %d; call "
+            "accblas_peer_disconnect and export again",
+            h->peer_world);
+        return ACCBLAS_ERR_INVALID;
+    }
     int rc = ensure_mailbox(h);
     if (rc != ACCBLAS_OK) {
         return rc;
     }
-    for (int i = 0; i < accblas::kMaxPeers; ++i) {
-        if (h->peer_mailbox[i] && h->peer_is_ipc[i]) {
-            cudaIpcCloseMemHandle(h->peer_mailbox[i]);
-        }
-        h->peer_mailbox[i] = nullptr;
-        h->peer_is_ipc[i] = false;
-    }
-    // a fresh group starts from a clean mailbox and epoch 0 on every rank
-    ACCBLAS_CUDA(cudaMemset(h->mailbox, 0, accblas::kMailboxBytes));
-    ACCBLAS_CUDA(cudaDeviceSynchronize());
     h->peer_world = world;
     h->peer_rank = rank;
     h->peer_epoch = 0;
@@ -430,7 +465,7 @@ int accblas_peer_connect_ipc(accblas_handle_t handle, int world, int rank,
     if (ipc_handles == nullptr) {
         return ACCBLAS_ERR_INVALID;
     }
-    int rc = peer_reset(h, world, rank);
+    int rc = peer_begin(h, world, rank);
     if (rc != ACCBLAS_OK) {
         return rc;
     }
@@ -441,8 +476,12 @@ int accblas_peer_connect_ipc(accblas_handle_t handle, int world, int rank,
         cudaIpcMemHandle_t ipc;
         memcpy(&ipc, static_cast<const char*>(ipc_handles) + 64 * r, 64);
         void* mapped = nullptr;
-        ACCBLAS_CUDA(cudaIpcOpenMemHandle(&mapped, ipc,
-                                          cudaIpcMemLazyEnablePeerAccess));
+        cudaError_t err = cudaIpcOpenMemHandle(&mapped, ipc,
+                                               cudaIpcMemLazyEnablePeerAccess);
+        if (err != cudaSuccess) {
+            peer_unmap(h);
+            return accblas::cuda_fail(err, "cudaIpcOpenMemHandle");
+        }
         h->peer_mailbox[r] = mapped;
         h->peer_is_ipc[r] = true;
     }
@@ -458,7 +497,7 @@ int accblas_peer_connect_ptrs(accblas_handle_t handle, int world, int rank,
     if (mailboxes == nullptr || devices == nullptr) {
         return ACCBLAS_ERR_INVALID;
     }
-    int rc = peer_reset(h, world, rank);
+    int rc = peer_begin(h, world, rank);
     if (rc != ACCBLAS_OK) {
         return rc;
     }
@@ -471,10 +510,66 @@ int accblas_peer_connect_ptrs(accblas_handle_t handle, int world, int rank,
             if (err == cudaErrorPeerAccessAlreadyEnabled) {
                 cudaGetLastError();
             } else if (err != cudaSuccess) {
+                peer_unmap(h);
                 return accblas::cuda_fail(err, "cudaDeviceEnablePeerAccess");
             }
         }
         h->peer_mailbox[r] = mailboxes[r];
+    }
+    return ACCBLAS_OK;
+}
+
+int accblas_peer_disconnect(accblas_handle_t handle)
+{
+    accblas_stream_t stream = nullptr;
+    ACCBLAS_ENTER(handle);
+    (void)s;
+    ACCBLAS_CUDA(cudaDeviceSynchronize());
+    peer_unmap(h);
+    if (h->mailbox) {
+        ACCBLAS_CUDA(cudaFree(h->mailbox));
+        h->mailbox = nullptr;
+    }
+    if (h->peer_status_host) {
+        *h->peer_status_host = 0ull;
+    }
+    return ACCBLAS_OK;
+}
+
+int accblas_peer_set_timeout(accblas_handle_t handle, double seconds)
+{
+    if (!accblas::check_handle(handle) || !(seconds >= 0.0) ||
+        seconds > 86400.0) {
+        accblas::set_error("peer timeout: 0 (wait for ever) ... 86400 s");
+        return ACCBLAS_ERR_INVALID;
+    }
+    reinterpret_cast<Handle*>(handle)->peer_timeout_ns =
+        static_cast<unsigned long long>(seconds * 1e9);
+    return ACCBLAS_OK;
+}
+
+int accblas_peer_status(accblas_handle_t handle,
+                        unsigned long long* failed_call)
+{
+    if (!accblas::check_handle(handle)) {
+        return ACCBLAS_ERR_INVALID;
+    }
+    Handle* h = reinterpret_cast<Handle*>(handle);
+    const unsigned long long failed =
+        h->peer_status_host
+            ? *reinterpret_cast<volatile unsigned long long*>(
+                  h->peer_status_host)
+            : 0ull;
+    if (failed_call != nullptr) {
+        *failed_call = failed;
+    }
+    if (failed != 0ull) {
+        accblas::set_error(
+            "dot_allreduce call #%llu: a peer did not publish its partial "
+            "within %.1f s; this rank's result of that call is NaN and the "
+            "group is out of step (disconnect and form a new group)",
+            failed, h->peer_timeout_ns * 1e-9);
+        return ACCBLAS_ERR_PEER;
     }
     return ACCBLAS_OK;
 }
@@ -497,10 +592,18 @@ int accblas_dot_allreduce(accblas_handle_t handle, accblas_dtype ar,
         accblas::set_error("dot_allreduce: call accblas_peer_connect_* first");
         return ACCBLAS_ERR_INVALID;
     }
+    // an earlier call on this handle timed out: the ranks no longer agree on
+    // the epoch, nothing is launched (sticky until accblas_peer_disconnect)
+    int rc = accblas_peer_status(handle, nullptr);
+    if (rc != ACCBLAS_OK) {
+        return rc;
+    }
     accblas::PeerExchange px;
     px.world = h->peer_world;
     px.rank = h->peer_rank;
     px.epoch = ++h->peer_epoch;
+    px.timeout_ns = h->peer_timeout_ns;
+    px.status = h->peer_status_dev;
     for (int r = 0; r < px.world; ++r) {
         px.mailbox[r] = h->peer_mailbox[r];
     }
@@ -724,46 +827,52 @@ int accblas_dev_gemv_trace(unsigned long long* trace)
 }
 
 // Development knob (not part of the drop-in surface): set a launch-shape
-// parameter by name.  Returns ACCBLAS_ERR_INVALID for unknown keys.
+// parameter by name.  Unknown keys and out-of-range values are rejected.
 int accblas_tune(const char* key, int value)
 {
-    accblas::Tuning& t = accblas::tuning();
+    using accblas::Tuning;
+    struct Knob {
+        const char* name;
+        int Tuning::*field;
+        int lo, hi;
+    };
+    static const Knob knobs[] = {
+        {"dot_unroll", &Tuning::dot_unroll, 0, 4},
+        {"dot_block", &Tuning::dot_block, 0, 1024},
+        {"dot_ctas_per_sm", &Tuning::dot_ctas_per_sm, 0, 32},
+        {"dot_pdl", &Tuning::dot_pdl, 0, 1},
+        {"dot_intmix", &Tuning::dot_intmix, 0, 1},
+        {"gemv_unroll", &Tuning::gemv_unroll, 0, 4},
+        {"gemv_variant", &Tuning::gemv_variant, 0, 5},
+        {"gemv_ctas_per_sm", &Tuning::gemv_ctas_per_sm, 0, 32},
+        {"gemv_pipe", &Tuning::gemv_pipe, -1, 4},
+        {"gemv_intwords", &Tuning::gemv_intwords, 0, 4},
+        {"gemv_pdl", &Tuning::gemv_pdl, 0, 1},
+        {"gemv_force_pieces", &Tuning::gemv_force_pieces, -1, 8},
+        {"gemv_taper", &Tuning::gemv_taper, 0, 1},
+        {"gemv_stages", &Tuning::gemv_stages, 0, 4},
+        {"gemv_rows8", &Tuning::gemv_rows8, 0, 1},
+        {"trsv_variant", &Tuning::trsv_variant, 0, 1},
+        {"trsv_whole_block_spin", &Tuning::trsv_whole_block_spin, 0, 1},
+        {"trsv_l2_ahead", &Tuning::trsv_l2_ahead, 0, 1 << 20},
+        {"fill_generic", &Tuning::fill_generic, 0, 1},
+    };
     if (key == nullptr) {
         return ACCBLAS_ERR_INVALID;
     }
-    if (!strcmp(key, "dot_unroll")) {
-        t.dot_unroll = value;
-    } else if (!strcmp(key, "dot_ctas_per_sm")) {
-        t.dot_ctas_per_sm = value;
-    } else if (!strcmp(key, "gemv_unroll")) {
-        t.gemv_unroll = value;
-    } else if (!strcmp(key, "gemv_variant")) {
-        t.gemv_variant = value;
-    } else if (!strcmp(key, "gemv_ctas_per_sm")) {
-        t.gemv_ctas_per_sm = value;
-    } else if (!strcmp(key, "gemv_stages")) {
-        t.gemv_stages = value;
-    } else if (!strcmp(key, "gemv_taper")) {
-        t.gemv_taper = value;
-    } else if (!strcmp(key, "dot_pdl")) {
-        t.dot_pdl = value;
-    } else if (!strcmp(key, "gemv_force_pieces")) {
-        t.gemv_force_pieces = value;
-    } else if (!strcmp(key, "gemv_pdl")) {
-        t.gemv_pdl = value;
-    } else if (!strcmp(key, "gemv_pipe")) {
-        t.gemv_pipe = value;
-    } else if (!strcmp(key, "gemv_intwords")) {
-        t.gemv_intwords = value;
-    } else if (!strcmp(key, "trsv_whole_block_spin")) {
-        t.trsv_whole_block_spin = value;
-    } else if (!strcmp(key, "trsv_l2_ahead")) {
-        t.trsv_l2_ahead = value;
-    } else {
-        accblas::set_error("unknown tuning key '%s'", key);
-        return ACCBLAS_ERR_INVALID;
+    for (const Knob& k : knobs) {
+        if (strcmp(key, k.name) == 0) {
+            if (value < k.lo || value > k.hi) {
+                accblas::set_error("tuning key '%s': %d outside [%d, %d]", key,
+                                   value, k.lo, k.hi);
+                return ACCBLAS_ERR_INVALID;
+            }
+            accblas::tuning().*(k.field) = value;
+            return ACCBLAS_OK;
+        }
     }
-    return ACCBLAS_OK;
+    accblas::set_error("unknown tuning key '%s'", key);
+    return ACCBLAS_ERR_INVALID;
 }
 
 }  // extern "C"

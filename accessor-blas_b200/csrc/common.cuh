@@ -36,6 +36,14 @@ struct Handle {
     int peer_world = 0;
     int peer_rank = 0;
     unsigned long long peer_epoch = 0;
+    // sticky failure word of the exchange: mapped pinned host memory the
+    // kernel writes (system scope) when a peer did not arrive in time; the
+    // host reads it at the start of every call without synchronising
+    unsigned long long* peer_status_host = nullptr;
+    unsigned long long* peer_status_dev = nullptr;
+    unsigned long long peer_timeout_ns = 30000000000ull;  // 30 s
+    // per-device launch constants of the DOT kernels (queried once)
+    int dot_regs_checked = 0;
 };
 
 // What the last CTA of a DOT needs to combine the per-GPU partials itself:
@@ -49,6 +57,8 @@ struct PeerExchange {
     int world = 0;
     int rank = 0;
     unsigned long long epoch = 0;
+    unsigned long long timeout_ns = 0;       // 0 = wait for ever
+    unsigned long long* status = nullptr;    // device alias of the failure word
     void* mailbox[kMaxPeers] = {};
 };
 
@@ -226,6 +236,62 @@ __device__ __forceinline__ uint4 ldg_cached_128_ordered(const void* p)
     asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
+    return r;
+}
+
+// 16 bytes as 64- or 32-bit loads (volatile asm: keeps its place among the
+// other streaming loads); STREAM = do not allocate in L1
+template <int CB, bool STREAM>
+__device__ __forceinline__ uint4 ldg_pieces(const void* p)
+{
+    const char* c = static_cast<const char*>(p);
+    uint4 r;
+    if constexpr (CB == 16) {
+        return STREAM ? ldg_stream_128(p) : ldg_cached_128_ordered(p);
+    } else if constexpr (CB == 8) {
+        if constexpr (STREAM) {
+            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(r.x), "=r"(r.y) : "l"(c));
+            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(r.z), "=r"(r.w) : "l"(c + 8));
+        } else {
+            asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(r.x), "=r"(r.y) : "l"(c));
+            asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];"
+                         : "=r"(r.z), "=r"(r.w) : "l"(c + 8));
+        }
+    } else if constexpr (CB == 4) {
+        unsigned w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (STREAM) {
+                asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];"
+                             : "=r"(w[i]) : "l"(c + 4 * i));
+            } else {
+                asm volatile("ld.global.nc.u32 %0, [%1];"
+                             : "=r"(w[i]) : "l"(c + 4 * i));
+            }
+        }
+        r = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        // 2-byte aligned (fp16 rows with an odd stride): eight 16-bit loads,
+        // all in flight together, instead of the scalar kernel's one per turn
+        unsigned short hw[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if constexpr (STREAM) {
+                asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];"
+                             : "=h"(hw[i]) : "l"(c + 2 * i));
+            } else {
+                asm volatile("ld.global.nc.u16 %0, [%1];"
+                             : "=h"(hw[i]) : "l"(c + 2 * i));
+            }
+        }
+        r = make_uint4(hw[0] | (static_cast<unsigned>(hw[1]) << 16),
+                       hw[2] | (static_cast<unsigned>(hw[3]) << 16),
+                       hw[4] | (static_cast<unsigned>(hw[5]) << 16),
+                       hw[6] | (static_cast<unsigned>(hw[7]) << 16));
+    }
     return r;
 }
 

@@ -12,6 +12,7 @@
 //     can fill their own slab of the same global stream.
 //   * the reference's L1 error metric (cuda/utils.cuh:315-332).
 #include "common.cuh"
+#include "tuning.h"
 
 namespace accblas {
 namespace {
@@ -173,6 +174,122 @@ __device__ __forceinline__ double draw_uniform(std::uint64_t& state)
     return __dadd_rn(__dmul_rn(u, 2.0), -1.0);
 }
 
+// ---- streaming generator ---------------------------------------------------
+// Both factors of every product are below 2^31, so the 62-bit product is ONE
+// 32x32->64 multiply (IMAD.WIDE.U32) and the two folds are 32-bit adds.
+__host__ __device__ __forceinline__ std::uint32_t mulmod31(std::uint32_t a,
+                                                           std::uint32_t b)
+{
+    const std::uint64_t v = std::uint64_t{a} * b;
+    const std::uint32_t m = static_cast<std::uint32_t>(kLcgM);
+    std::uint32_t t = (static_cast<std::uint32_t>(v) & m) +
+                      static_cast<std::uint32_t>(v >> 31);  // < 2^32
+    t = (t & m) + (t >> 31);                                // <= m + 1
+    return t >= m ? t - m : t;
+}
+
+// 16807^e mod (2^31 - 1); the exponent is first reduced modulo the group
+// order 2^31 - 2 (the modulus is prime), which bounds the loop at 31 turns
+__host__ __device__ __forceinline__ std::uint32_t pow_a31(std::uint64_t e)
+{
+    e %= (kLcgM - 1);
+    std::uint32_t base = static_cast<std::uint32_t>(kLcgA), r = 1;
+    while (e) {
+        if (e & 1) {
+            r = mulmod31(r, base);
+        }
+        base = mulmod31(base, base);
+        e >>= 1;
+    }
+    return r;
+}
+
+// Same value as draw_uniform, with the quotient sum / RR formed as
+//   q = RN(sum * y), r = sum - q * RR (exact in an FMA), u = RN(q + r * y),
+// y = RN(1 / RR): the classic correctly-rounded division by a constant
+// (Markstein; y is the correctly rounded reciprocal, q is within one ulp of
+// the quotient, so the corrected u IS the rounded quotient) -- three FP64
+// instructions instead of the ~25 of the general division routine.
+// tests/test_gpu_parity.py::test_fill_fast_equals_generic compares 2^27 draws
+// of this path with the __ddiv_rn one bit for bit.
+__device__ __forceinline__ double draw_uniform_fast(std::uint32_t& state)
+{
+    const double R = 2147483646.0;
+    const double RR = 4611686009837453316.0;
+    constexpr double kInvRR = 1.0 / 4611686009837453316.0;  // RN at compile time
+    state = mulmod31(state, static_cast<std::uint32_t>(kLcgA));
+    const double lo = static_cast<double>(static_cast<int>(state - 1));
+    state = mulmod31(state, static_cast<std::uint32_t>(kLcgA));
+    const double hi = static_cast<double>(static_cast<int>(state - 1));
+    const double sum = __dadd_rn(lo, __dmul_rn(hi, R));
+    const double q = __dmul_rn(sum, kInvRR);
+    const double rem = __fma_rn(-q, RR, sum);
+    double u = __fma_rn(rem, kInvRR, q);
+    if (u >= 1.0) {
+        u = __longlong_as_double(0x3FEFFFFFFFFFFFFFLL);
+    }
+    // 2u is exact, so this FMA rounds exactly like (u * 2.0) + (-1.0)
+    return __fma_rn(u, 2.0, -1.0);
+}
+
+// Contiguous output: thread t owns the 4-draw groups t, t + T, t + 2T, ...
+// (T = threads in the grid).  ONE modular exponentiation per thread positions
+// the engine at its first group; after the 8 engine calls of a group the
+// state is moved to the thread's next group with a single multiplication by
+// the launch constant 16807^(8(T-1)).  Stores are 16-byte vectors, fully
+// coalesced.  (The per-row kernel below redoes the exponentiation for every 4
+// draws: 258 GB/s on B200; it remains for strided / unaligned outputs.)
+template <typename Dst>
+__global__ __launch_bounds__(256) void fill_linear_kernel(
+    std::int64_t count, Dst* __restrict__ out, std::uint32_t seed_state,
+    std::uint64_t first_draw, std::uint32_t jump,
+    unsigned* __restrict__ bad_counter)
+{
+    const std::int64_t threads = std::int64_t{gridDim.x} * 256;
+    std::int64_t p =
+        (std::int64_t{blockIdx.x} * 256 + threadIdx.x) * kElemsPerThread;
+    if (p >= count) {
+        return;
+    }
+    std::uint32_t state = mulmod31(
+        pow_a31(2 * (first_draw + static_cast<std::uint64_t>(p))), seed_state);
+    unsigned bad = 0;
+    for (; p < count; p += threads * kElemsPerThread) {
+        Pack<Dst, kElemsPerThread> q;
+        double v[kElemsPerThread];
+#pragma unroll
+        for (int i = 0; i < kElemsPerThread; ++i) {
+            v[i] = draw_uniform_fast(state);
+            q.v[i] = cast_one<Dst, double>(v[i]);
+        }
+        const int valid = (count - p >= kElemsPerThread)
+                              ? kElemsPerThread
+                              : static_cast<int>(count - p);
+#pragma unroll
+        for (int i = 0; i < kElemsPerThread; ++i) {
+            const double av = fabs(v[i]);
+            bad += (i >= valid || (av >= 2.2250738585072014e-308 &&
+                                   av <= 1.7976931348623157e308))
+                       ? 0u
+                       : 1u;
+        }
+        if (valid == kElemsPerThread) {
+            *reinterpret_cast<Pack<Dst, kElemsPerThread>*>(out + p) = q;
+        } else {
+#pragma unroll
+            for (int i = 0; i < kElemsPerThread; ++i) {
+                if (i < valid) {
+                    out[p + i] = q.v[i];
+                }
+            }
+        }
+        state = mulmod31(state, jump);
+    }
+    if (bad) {
+        atomicAdd(bad_counter, bad);
+    }
+}
+
 template <typename Dst>
 __global__ __launch_bounds__(256) void fill_uniform_kernel(
     std::int64_t rows, std::int64_t cols, Dst* __restrict__ out,
@@ -229,12 +346,32 @@ int launch_fill(Handle* h, std::int64_t rows, std::int64_t cols, void* out,
     }
     unsigned* flag = control_words(h) + kCtlFillFlag;
     ACCBLAS_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned), stream));
-    const std::int64_t per_block = 256 * kElemsPerThread;
-    const std::int64_t gx = (cols + per_block - 1) / per_block;
-    const std::int64_t gy = rows < 32768 ? rows : 32768;
-    const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy));
-    fill_uniform_kernel<Dst><<<grid, 256, 0, stream>>>(
-        rows, cols, static_cast<Dst*>(out), ld, s0, first_draw, flag);
+    const bool contiguous = (ld == cols) || rows == 1;
+    const bool aligned =
+        reinterpret_cast<std::uintptr_t>(out) %
+            (sizeof(Dst) * kElemsPerThread) == 0;
+    if (contiguous && aligned && tuning().fill_generic == 0) {
+        const std::int64_t count = rows * cols;
+        const std::int64_t groups =
+            (count + kElemsPerThread - 1) / kElemsPerThread;
+        std::int64_t grid = (groups + 255) / 256;
+        const std::int64_t cap = std::int64_t{h->sm_count} * 16;
+        grid = grid > cap ? cap : grid;
+        const std::uint64_t threads = static_cast<std::uint64_t>(grid) * 256;
+        // engine calls between the end of one group and the start of the
+        // thread's next one: 2 * 4 * (T - 1)
+        const std::uint32_t jump = pow_a31(8 * (threads - 1));
+        fill_linear_kernel<Dst><<<static_cast<unsigned>(grid), 256, 0, stream>>>(
+            count, static_cast<Dst*>(out), static_cast<std::uint32_t>(s0),
+            first_draw, jump, flag);
+    } else {
+        const std::int64_t per_block = 256 * kElemsPerThread;
+        const std::int64_t gx = (cols + per_block - 1) / per_block;
+        const std::int64_t gy = rows < 32768 ? rows : 32768;
+        const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy));
+        fill_uniform_kernel<Dst><<<grid, 256, 0, stream>>>(
+            rows, cols, static_cast<Dst*>(out), ld, s0, first_draw, flag);
+    }
     ACCBLAS_CUDA(cudaGetLastError());
     unsigned bad = 0;
     ACCBLAS_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(unsigned),

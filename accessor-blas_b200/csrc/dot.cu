@@ -11,8 +11,16 @@
 //   pass 2  the CTA that finishes last (completion counter) folds the partials
 //           in a fixed order with the same tree, converts to the result type
 //           and re-arms the counter.
-// The summation order depends only on (n, dtype pair, grid), never on which
-// CTA happens to be last, so the result is bit-reproducible run to run.
+// The summation order depends only on (n, dtype pair, launch shape), never on
+// which CTA happens to be last, so the result is bit-reproducible run to run.
+//
+// Operand layouts on the vector path: contiguous operands with the same
+// misalignment are peeled to the first 16-byte boundary; contiguous operands
+// with DIFFERENT misalignments stream the better aligned one with 128-bit
+// loads and fetch the other one's 16 bytes in 8- / 4- / 2-byte pieces (same
+// registers afterwards, so the arithmetic and its order are those of the
+// aligned kernel).  Strided operands use scalar loads, four of each operand in
+// flight per thread.
 #include "common.cuh"
 #include "tuning.h"
 
@@ -37,6 +45,30 @@ struct pair_fma<double, __half> {
     {
         const float p = __fmul_rn(__half2float(a), __half2float(b));
         return __dadd_rn(acc, static_cast<double>(p));
+    }
+};
+
+// fp32 -> fp64 off the conversion pipe (experiment, `dot_intmix`).  The 32
+// bits of a float f, shifted right by three into the high word of a double
+// (sign kept at bit 31, the three replicated sign bits cleared), read as
+//     d = value(f) * 2^-896
+// for zero, subnormal and normal f alike: the 8-bit exponent lands in the low
+// 8 bits of the 11-bit field.  One signed 32x32->64 multiply by 2^29 builds the
+// register pair, one mask cleans the high word.  x goes this way, y through
+// F2F; the accumulator then holds sum * 2^-896 and is scaled back once per
+// thread (exact).  Inf/NaN inputs do not map: 0 * f on the fp32 pipe is NaN
+// exactly for those, and the CTA falls back to ordinary conversions.
+struct FloatToDoubleScaled {
+    static __device__ __forceinline__ double widen(unsigned f)
+    {
+        long long p;
+        asm("mul.wide.s32 %0, %1, 0x20000000;" : "=l"(p) : "r"(f));
+        return __longlong_as_double(
+            p & static_cast<long long>(0x8FFFFFFFFFFFFFFFull));
+    }
+    static __device__ __forceinline__ double unscale()
+    {
+        return __hiloint2double((896 + 1023) << 20, 0);  // 2^896
     }
 };
 
@@ -94,7 +126,9 @@ __device__ __forceinline__ unsigned long long dot_globaltimer_ns()
 // Fused all-reduce of the per-GPU partials (one thread per peer): store my
 // partial into every peer's mailbox (P2P stores over NVLink), then wait for the
 // peer's entry in mine.  Returns the sum in rank order (valid in thread 0).
-// A peer that never shows up (2 s) yields NaN instead of a hung GPU.
+// A peer that does not show up within px.timeout_ns yields NaN on this rank
+// AND raises the handle's sticky failure word (mapped host memory), so the
+// next call on the handle returns ACCBLAS_ERR_PEER instead of launching.
 template <typename Ar>
 __device__ __forceinline__ Ar peer_allreduce(Ar mine, const PeerExchange& px)
 {
@@ -120,7 +154,8 @@ __device__ __forceinline__ Ar peer_allreduce(Ar mine, const PeerExchange& px)
         const unsigned long long t0 = dot_globaltimer_ns();
         bool ok = true;
         while (in[1] != px.epoch) {
-            if (dot_globaltimer_ns() - t0 > 2000000000ull) {
+            if (px.timeout_ns != 0 &&
+                dot_globaltimer_ns() - t0 > px.timeout_ns) {
                 ok = false;
                 break;
             }
@@ -128,6 +163,11 @@ __device__ __forceinline__ Ar peer_allreduce(Ar mine, const PeerExchange& px)
         __threadfence_system();  // flag before value
         peer_vals[t] = ok ? __longlong_as_double(static_cast<long long>(in[0]))
                           : __longlong_as_double(0x7ff8000000000000LL);
+        if (!ok && px.status != nullptr) {
+            *reinterpret_cast<volatile unsigned long long*>(px.status) =
+                px.epoch;
+            __threadfence_system();
+        }
     }
     __syncthreads();
     Ar total = Ar{};
@@ -139,7 +179,7 @@ __device__ __forceinline__ Ar peer_allreduce(Ar mine, const PeerExchange& px)
     return total;
 }
 
-// Second pass + epilogue shared by both first-pass kernels.
+// Second pass + epilogue shared by all first-pass kernels.
 template <typename Ar, int BLOCK>
 __device__ __forceinline__ void finish_dot(Ar local, Ar* partials,
                                            unsigned* counter, void* result,
@@ -175,17 +215,19 @@ __device__ __forceinline__ void finish_dot(Ar local, Ar* partials,
     }
 }
 
-// Contiguous, 16-byte aligned operands.
-template <typename St, typename Ar, int BLOCK, int UNROLL>
+// Contiguous operands.  x is 16-byte aligned (after peeling `head` elements);
+// y is aligned to CBY bytes (16 = the same alignment as x).
+// MIX (fp32 storage, fp64 arithmetic only): x widened on the integer pipes.
+template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX>
 __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     const St* __restrict__ x, const St* __restrict__ y, std::int64_t n,
     Ar* __restrict__ partials, unsigned* __restrict__ counter,
     void* __restrict__ result, int res_dtype, const PeerExchange px, int pdl,
     int head)
 {
-    // x and y point at the first 16-byte aligned element; `head` (< 16 /
-    // sizeof(St)) elements in front of it belong to the operands as well
-    // (both vectors misaligned by the same amount, e.g. x[1:] . y[1:])
+    // x and y point at the element that falls on x's first 16-byte boundary;
+    // `head` (< 16 / sizeof(St)) elements in front of it belong to the operands
+    // as well (e.g. x[1:] . y[1:])
     constexpr int VEC = vec_traits<St>::elems;
     constexpr std::int64_t TILE = std::int64_t{BLOCK} * VEC * UNROLL;
     __shared__ Ar scratch[kWarp];
@@ -224,6 +266,7 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
             acc[u][i] = Ar{};
         }
     }
+    float chk = 0.0f;  // MIX: NaN iff an Inf/NaN went through the scaled path
 
     for (std::int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const std::int64_t base = tile * TILE + std::int64_t{threadIdx.x} * VEC;
@@ -235,15 +278,62 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            yr[u] = ldg_stream_128(y + base + std::int64_t{u} * BLOCK * VEC);
+            yr[u] = ldg_pieces<CBY, true>(y + base +
+                                          std::int64_t{u} * BLOCK * VEC);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
+            if constexpr (MIX) {
+                const unsigned xw[4] = {xr[u].x, xr[u].y, xr[u].z, xr[u].w};
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                acc[u][i % SLOTS] = pair_fma<Ar, St>::apply(
-                    raw_elem<St>(xr[u], i), raw_elem<St>(yr[u], i),
-                    acc[u][i % SLOTS]);
+                for (int i = 0; i < 4; ++i) {
+                    const double xs = FloatToDoubleScaled::widen(xw[i]);
+                    acc[u][0] = fma(
+                        xs, static_cast<double>(raw_elem<float>(yr[u], i)),
+                        acc[u][0]);
+                    chk = fmaf(__uint_as_float(xw[i]), 0.0f, chk);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    acc[u][i % SLOTS] = pair_fma<Ar, St>::apply(
+                        raw_elem<St>(xr[u], i), raw_elem<St>(yr[u], i),
+                        acc[u][i % SLOTS]);
+                }
+            }
+        }
+    }
+    if constexpr (MIX) {
+        // (block-uniform) an Inf/NaN was consumed by the scaled conversion:
+        // redo this CTA's tiles with ordinary conversions
+        const bool bad = __syncthreads_or(chk != chk);
+        if (bad) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                acc[u][0] = 0.0;
+            }
+            for (std::int64_t tile = blockIdx.x; tile < num_tiles;
+                 tile += gridDim.x) {
+                const std::int64_t base =
+                    tile * TILE + std::int64_t{threadIdx.x} * VEC;
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const uint4 xv =
+                        ldg_stream_128(x + base + std::int64_t{u} * BLOCK * VEC);
+                    const uint4 yv = ldg_pieces<CBY, true>(
+                        y + base + std::int64_t{u} * BLOCK * VEC);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        acc[u][0] = pair_fma<Ar, St>::apply(
+                            raw_elem<St>(xv, i), raw_elem<St>(yv, i), acc[u][0]);
+                    }
+                }
+            }
+        } else {
+            const double s = FloatToDoubleScaled::unscale();
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                acc[u][0] = acc[u][0] * s;
             }
         }
     }
@@ -284,8 +374,9 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
                           px);
 }
 
-// Any stride / alignment: scalar loads, 64-bit indices (the reference's plain
-// kernel is limited to int32, cuda/dot_kernels.cuh:89-97).
+// Any stride: scalar loads, four of each operand in flight per thread, 64-bit
+// indices (the reference's plain kernel is limited to int32,
+// cuda/dot_kernels.cuh:89-97).
 template <typename St, typename Ar, int BLOCK>
 __global__ __launch_bounds__(BLOCK) void dot_strided_kernel(
     const St* __restrict__ x, std::int64_t incx, const St* __restrict__ y,
@@ -293,39 +384,60 @@ __global__ __launch_bounds__(BLOCK) void dot_strided_kernel(
     unsigned* __restrict__ counter, void* __restrict__ result, int res_dtype,
     const PeerExchange px)
 {
+    constexpr int U = 4;
     __shared__ Ar scratch[kWarp];
-    Ar acc0 = Ar{}, acc1 = Ar{};
+    Ar acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        acc[u] = Ar{};
+    }
     const std::int64_t step = std::int64_t{gridDim.x} * BLOCK;
     std::int64_t i = std::int64_t{blockIdx.x} * BLOCK + threadIdx.x;
-    for (; i + step < n; i += 2 * step) {
-        const St xa = x[i * incx], ya = y[i * incy];
-        const St xb = x[(i + step) * incx], yb = y[(i + step) * incy];
-        acc0 = pair_fma<Ar, St>::apply(xa, ya, acc0);
-        acc1 = pair_fma<Ar, St>::apply(xb, yb, acc1);
+    for (; i + (U - 1) * step < n; i += U * step) {
+        St xa[U], ya[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            xa[u] = x[(i + u * step) * incx];
+            ya[u] = y[(i + u * step) * incy];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            acc[u] = pair_fma<Ar, St>::apply(xa[u], ya[u], acc[u]);
+        }
     }
-    if (i < n) {
-        acc0 = pair_fma<Ar, St>::apply(x[i * incx], y[i * incy], acc0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (i + u * step < n) {
+            acc[u] = pair_fma<Ar, St>::apply(x[(i + u * step) * incx],
+                                             y[(i + u * step) * incy], acc[u]);
+        }
     }
-    finish_dot<Ar, BLOCK>(acc0 + acc1, partials, counter, result, res_dtype,
-                          scratch, px);
+    finish_dot<Ar, BLOCK>((acc[0] + acc[1]) + (acc[2] + acc[3]), partials,
+                          counter, result, res_dtype, scratch, px);
 }
 
-template <typename St, typename Ar, int BLOCK, int UNROLL>
+template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX>
 int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
                   void* result, int res, int ctas_per_sm, cudaStream_t stream,
                   const PeerExchange& px, int head)
 {
     constexpr int VEC = vec_traits<St>::elems;
     constexpr std::int64_t TILE = std::int64_t{BLOCK} * VEC * UNROLL;
-    auto kernel = dot_stream_kernel<St, Ar, BLOCK, UNROLL>;
+    auto kernel = dot_stream_kernel<St, Ar, BLOCK, UNROLL, CBY, MIX>;
     // one resident wave: every CTA of the grid-stride loop is on the machine
-    // from start to end (a partial second wave would leave a tail)
-    static int resident = 0;  // per instantiation
-    if (resident == 0) {
+    // from start to end (a partial second wave would leave a tail).  The
+    // occupancy is a property of (instantiation, device).
+    static int resident_on[64] = {};
+    const int slot = (h->device >= 0 && h->device < 64) ? h->device : 0;
+    int resident = resident_on[slot];
+    if (resident == 0 || slot != h->device) {
         int occ = 0;
         ACCBLAS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
             &occ, kernel, BLOCK, 0));
         resident = occ > 0 ? occ : 1;
+        if (slot == h->device) {
+            resident_on[slot] = resident;
+        }
     }
     if (ctas_per_sm <= 0 || ctas_per_sm > resident) {
         ctas_per_sm = resident;
@@ -360,42 +472,93 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
     return ACCBLAS_OK;
 }
 
+// launch shape of the aligned kernel: CTA size and vectors in flight, from the
+// tuning knobs (0 = the per-pair default measured on B200)
+template <typename St, typename Ar, bool MIX>
+int launch_shape(Handle* h, std::int64_t n, const void* x, const void* y,
+                 void* result, int res, cudaStream_t stream,
+                 const PeerExchange& px, int head)
+{
+    const Tuning& t = tuning();
+    int unroll = t.dot_unroll;
+    int block = t.dot_block;
+    if (unroll == 0) {
+        // same-box sweeps (tools/tune.py dot): 8-byte elements and halves like
+        // two vectors per operand in flight, fp32 storage four
+        unroll = sizeof(St) == 4 ? 4 : 2;
+    }
+    if (block == 0) {
+        block = 256;
+    }
+    const int cps = t.dot_ctas_per_sm;
+#define ACCBLAS_DOT_SHAPE(B, U)                                               \
+    if (block == B && unroll == U) {                                          \
+        return launch_stream<St, Ar, B, U, 16, MIX>(h, n, x, y, result, res,  \
+                                                    cps, stream, px, head);   \
+    }
+    ACCBLAS_DOT_SHAPE(256, 2)
+    ACCBLAS_DOT_SHAPE(256, 4)
+    ACCBLAS_DOT_SHAPE(512, 2)
+    ACCBLAS_DOT_SHAPE(512, 4)
+    ACCBLAS_DOT_SHAPE(1024, 2)
+    ACCBLAS_DOT_SHAPE(1024, 4)
+#undef ACCBLAS_DOT_SHAPE
+    set_error("dot: no kernel for block=%d unroll=%d", block, unroll);
+    return ACCBLAS_ERR_INVALID;
+}
+
 template <typename St, typename Ar>
 int launch_dot(Handle* h, std::int64_t n, const void* x, std::int64_t incx,
                const void* y, std::int64_t incy, void* result, int res,
                cudaStream_t stream, const PeerExchange& px)
 {
-    // contiguous operands with the SAME misalignment: peel the elements in
-    // front of the first 16-byte boundary, stream the rest
-    const std::uintptr_t xa = reinterpret_cast<std::uintptr_t>(x);
-    const std::uintptr_t ya = reinterpret_cast<std::uintptr_t>(y);
-    int head = 0;
-    bool aligned = ((xa | ya) & 15u) == 0;
-    if (!aligned && incx == 1 && incy == 1 && (xa & 15u) == (ya & 15u) &&
-        (xa % sizeof(St)) == 0) {
-        head = static_cast<int>((16u - (xa & 15u)) / sizeof(St));
-        if (head <= n) {
-            aligned = true;
-            x = static_cast<const St*>(x) + head;
-            y = static_cast<const St*>(y) + head;
-            n -= head;
-        } else {
-            head = 0;
-        }
-    }
-    if (incx == 1 && incy == 1 && aligned) {
-        const int unroll = tuning().dot_unroll;
-        const int cps = tuning().dot_ctas_per_sm;
-        switch (unroll) {
-        case 2:
-            return launch_stream<St, Ar, 256, 2>(h, n, x, y, result, res, cps,
-                                                 stream, px, head);
-        case 8:
-            return launch_stream<St, Ar, 256, 8>(h, n, x, y, result, res, cps,
-                                                 stream, px, head);
-        default:
-            return launch_stream<St, Ar, 256, 4>(h, n, x, y, result, res, cps,
-                                                 stream, px, head);
+    if (incx == 1 && incy == 1) {
+        std::uintptr_t xa = reinterpret_cast<std::uintptr_t>(x);
+        std::uintptr_t ya = reinterpret_cast<std::uintptr_t>(y);
+        if (xa % sizeof(St) == 0 && ya % sizeof(St) == 0) {
+            const auto low = [](std::uintptr_t a) {
+                return static_cast<unsigned>(a & 15u);
+            };
+            // peel so that x sits on a 16-byte boundary
+            int head = 0;
+            if (low(xa) != 0) {
+                head = static_cast<int>((16u - low(xa)) / sizeof(St));
+            }
+            if (head <= n) {
+                const St* xp = static_cast<const St*>(x) + head;
+                const St* yp = static_cast<const St*>(y) + head;
+                const unsigned dy =
+                    low(reinterpret_cast<std::uintptr_t>(yp));
+                const std::int64_t rest = n - head;
+                if (dy == 0) {
+                    if constexpr (std::is_same<St, float>::value &&
+                                  std::is_same<Ar, double>::value) {
+                        if (tuning().dot_intmix != 0) {
+                            return launch_shape<St, Ar, true>(
+                                h, rest, xp, yp, result, res, stream, px, head);
+                        }
+                    }
+                    return launch_shape<St, Ar, false>(h, rest, xp, yp, result,
+                                                       res, stream, px, head);
+                }
+                // different misalignments: y in pieces of its own alignment
+                const int cps = tuning().dot_ctas_per_sm;
+                if (dy % 8 == 0) {
+                    return launch_stream<St, Ar, 256, 4, 8, false>(
+                        h, rest, xp, yp, result, res, cps, stream, px, head);
+                }
+                if constexpr (sizeof(St) <= 4) {
+                    if (dy % 4 == 0) {
+                        return launch_stream<St, Ar, 256, 4, 4, false>(
+                            h, rest, xp, yp, result, res, cps, stream, px,
+                            head);
+                    }
+                }
+                if constexpr (sizeof(St) == 2) {
+                    return launch_stream<St, Ar, 256, 4, 2, false>(
+                        h, rest, xp, yp, result, res, cps, stream, px, head);
+                }
+            }
         }
     }
     constexpr int BLOCK = 256;

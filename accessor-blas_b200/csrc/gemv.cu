@@ -232,60 +232,6 @@ __device__ __forceinline__ double half_bits_to_double(unsigned short bits)
     return d;
 }
 
-// 16 bytes as 64- or 32-bit loads (volatile asm: keeps its place among the
-// other streaming loads); STREAM = do not allocate in L1
-template <int CB, bool STREAM>
-__device__ __forceinline__ uint4 ldg_pieces(const void* p)
-{
-    const char* c = static_cast<const char*>(p);
-    uint4 r;
-    if constexpr (CB == 8) {
-        if constexpr (STREAM) {
-            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];"
-                         : "=r"(r.x), "=r"(r.y) : "l"(c));
-            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];"
-                         : "=r"(r.z), "=r"(r.w) : "l"(c + 8));
-        } else {
-            asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];"
-                         : "=r"(r.x), "=r"(r.y) : "l"(c));
-            asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];"
-                         : "=r"(r.z), "=r"(r.w) : "l"(c + 8));
-        }
-    } else if constexpr (CB == 4) {
-        unsigned w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if constexpr (STREAM) {
-                asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];"
-                             : "=r"(w[i]) : "l"(c + 4 * i));
-            } else {
-                asm volatile("ld.global.nc.u32 %0, [%1];"
-                             : "=r"(w[i]) : "l"(c + 4 * i));
-            }
-        }
-        r = make_uint4(w[0], w[1], w[2], w[3]);
-    } else {
-        // 2-byte aligned (fp16 rows with an odd stride): eight 16-bit loads,
-        // all in flight together, instead of the scalar kernel's one per turn
-        unsigned short hw[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if constexpr (STREAM) {
-                asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];"
-                             : "=h"(hw[i]) : "l"(c + 2 * i));
-            } else {
-                asm volatile("ld.global.nc.u16 %0, [%1];"
-                             : "=h"(hw[i]) : "l"(c + 2 * i));
-            }
-        }
-        r = make_uint4(hw[0] | (static_cast<unsigned>(hw[1]) << 16),
-                       hw[2] | (static_cast<unsigned>(hw[3]) << 16),
-                       hw[4] | (static_cast<unsigned>(hw[5]) << 16),
-                       hw[6] | (static_cast<unsigned>(hw[7]) << 16));
-    }
-    return r;
-}
-
 // One "batch" = one 128-bit vector per lane from each of the ROWS rows plus the
 // matching vector of x: 32 * VEC consecutive columns.  The streaming loop keeps
 // one batch in flight while the previous one is being consumed (software

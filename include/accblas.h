@@ -50,7 +50,8 @@ typedef enum accblas_status {
     ACCBLAS_ERR_UNSUPPORTED = 2, /* dtype combination not instantiated (e.g. fp16 arithmetic) */
     ACCBLAS_ERR_CUDA = 3,        /* a CUDA runtime call or kernel launch failed */
     ACCBLAS_ERR_ALLOC = 4,       /* workspace allocation failed */
-    ACCBLAS_ERR_DATA = 5         /* data-dependent failure (non-normal draw in fill_uniform) */
+    ACCBLAS_ERR_DATA = 5,        /* data-dependent failure (non-normal draw in fill_uniform) */
+    ACCBLAS_ERR_PEER = 6         /* multi-GPU exchange: a peer did not arrive within the time limit */
 } accblas_status;
 
 /* which triangle of the row-major matrix / whether the diagonal is implied
@@ -102,17 +103,39 @@ int accblas_dot(accblas_handle_t handle, accblas_dtype ar, accblas_dtype st,
  * mailbox and sums them in rank order, so *result (as `res`) is the dot
  * product of the whole vectors on every rank, with identical bits on all of
  * them -- one launch per rank, no separate collective.  At most 8 ranks.
+ *
  * Set-up, once per group: either (one process per GPU) every rank calls
  * accblas_peer_export, the 64-byte CUDA IPC handles are gathered in rank
  * order and passed to accblas_peer_connect_ipc; or (one process, several
- * handles) accblas_peer_mailbox + accblas_peer_connect_ptrs.  All ranks must
- * issue the same sequence of accblas_dot_allreduce calls. */
+ * handles) accblas_peer_mailbox + accblas_peer_connect_ptrs.  The mailbox is
+ * allocated and zeroed by export / mailbox and never cleared afterwards, so
+ * NO barrier is needed between connect and the first call: an entry a faster
+ * peer has already published stays where it is.  A handle belongs to one
+ * group at a time; accblas_peer_disconnect (after the group's last call has
+ * completed on every rank) frees the mailbox, and a new group starts from a
+ * fresh export.  All ranks must issue the same sequence of
+ * accblas_dot_allreduce calls.
+ *
+ * Failure: a peer that has not published its partial after the time limit
+ * (accblas_peer_set_timeout, default 30 s, 0 = wait for ever) makes THIS
+ * rank's result of that call NaN and raises a sticky failure word in mapped
+ * host memory.  From then on accblas_dot_allreduce on this handle returns
+ * ACCBLAS_ERR_PEER without launching (the ranks no longer agree on the call
+ * number); accblas_peer_status reports the failing call number at any time
+ * without synchronising.  Recovery: accblas_peer_disconnect on every rank and
+ * a new group, or fall back to accblas_dot + an external all-reduce. */
 int accblas_peer_export(accblas_handle_t handle, void* ipc_handle_64_bytes);
 int accblas_peer_connect_ipc(accblas_handle_t handle, int world, int rank,
                              const void* ipc_handles /* world x 64 bytes */);
 int accblas_peer_mailbox(accblas_handle_t handle, void** device_ptr);
 int accblas_peer_connect_ptrs(accblas_handle_t handle, int world, int rank,
                               void* const* mailboxes, const int* devices);
+int accblas_peer_disconnect(accblas_handle_t handle);
+int accblas_peer_set_timeout(accblas_handle_t handle, double seconds);
+/* ACCBLAS_OK, or ACCBLAS_ERR_PEER with *failed_call = number of the
+ * accblas_dot_allreduce call (counted from 1 since connect) that timed out */
+int accblas_peer_status(accblas_handle_t handle,
+                        unsigned long long* failed_call);
 int accblas_dot_allreduce(accblas_handle_t handle, accblas_dtype ar,
                           accblas_dtype st, accblas_dtype res, int64_t n,
                           const void* x, int64_t incx, const void* y,
@@ -173,9 +196,10 @@ int accblas_trsv_host(accblas_handle_t handle, accblas_dtype ar,
                       accblas_stream_t stream);
 
 /* Development knob, not part of the drop-in surface: sets a launch-shape
- * parameter ("dot_unroll", "dot_ctas_per_sm", "gemv_unroll", "gemv_variant",
- * "gemv_ctas_per_sm", "trsv_variant") process-wide.  Results are
- * bit-reproducible for a fixed configuration only. */
+ * parameter (the fields of accblas::Tuning, csrc/tuning.h, by name)
+ * process-wide; unknown keys and out-of-range values are rejected.  Not
+ * synchronised: set it while no other thread is inside the library.  Results
+ * are bit-reproducible for a fixed configuration only. */
 int accblas_tune(const char* key, int value);
 
 #ifdef __cplusplus
