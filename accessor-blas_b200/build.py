@@ -3,6 +3,9 @@
 Outputs (git-ignored, shipped to the GPU box by gpurun):
   accessor-blas_b200/libaccblas_b200.so        the product: kernels + C ABI
   accessor-blas_b200/libaccblas_baselines.so   cuBLAS baselines (bench only)
+  accessor-blas_b200/libaccblas_b200_dev.so    build_dev(): the product sources
+                                               with -DACCBLAS_DEV_HOOKS (timeline
+                                               probes for tools/*_trace.py)
 """
 from __future__ import annotations
 
@@ -20,7 +23,8 @@ BUILD = ROOT / "build" / "accblas"
 LIB = HERE / "libaccblas_b200.so"
 BASELINES_LIB = HERE / "libaccblas_baselines.so"
 
-KERNEL_SOURCES = ["capi.cu", "dot.cu", "gemv.cu", "trsv.cu", "convert_fill.cu"]
+KERNEL_SOURCES = ["capi.cu", "dot.cu", "gemv.cu", "trsv.cu", "trsv_cluster_f64.cu", "trsv_cluster_f32.cu",
+                  "convert_fill.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
@@ -86,6 +90,38 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+DEV_LIB = HERE / "libaccblas_b200_dev.so"
+
+
+def build_dev(force: bool = False, verbose: bool = False) -> Path:
+    """The same sources with the development hooks compiled in (phase
+    timestamps of TRSV / GEMV).  Used by tools/ only; the product library never
+    carries them."""
+    nvcc = _nvcc()
+    out = ROOT / "build" / "accblas_dev"
+    out.mkdir(parents=True, exist_ok=True)
+    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + \
+        list((ROOT / "include").glob("*.h"))
+
+    def compile_one(name: str) -> Path:
+        src = CSRC / name
+        obj = out / (src.stem + ".o")
+        if force or _stale(obj, [src] + headers):
+            cmd = [nvcc, *COMMON_FLAGS, "-DACCBLAS_DEV_HOOKS", *ARCH_FLAGS, "-c",
+                   str(src), "-o", str(obj)]
+            if verbose:
+                print(" ".join(cmd))
+            _run(cmd)
+        return obj
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as pool:
+        objs = list(pool.map(compile_one, KERNEL_SOURCES))
+    if force or _stale(DEV_LIB, objs):
+        _run([nvcc, "-shared", *ARCH_FLAGS, "-o", str(DEV_LIB), *map(str, objs),
+              "-cudart", "static"])
+    return DEV_LIB
+
+
 BIN = HERE / "bin"
 PROGRAMS = {
     # name: (source, extra link flags)
@@ -125,3 +161,5 @@ def build_programs(force: bool = False, verbose: bool = False) -> None:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    if "--dev" in sys.argv:
+        print(build_dev(force="--force" in sys.argv, verbose=True))

@@ -7,12 +7,15 @@ CPU.
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import (POINTER, c_char_p, c_double, c_int, c_int64, c_size_t,
                     c_uint32, c_uint64, c_void_p)
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libaccblas_b200.so"
+# ACCBLAS_LIB: development tools load libaccblas_b200_dev.so (same sources plus
+# the timeline probes) through the same binding
+LIB_PATH = Path(os.environ.get("ACCBLAS_LIB", HERE / "libaccblas_b200.so"))
 BASELINES_PATH = HERE / "libaccblas_baselines.so"
 
 F64, F32, F16 = 0, 1, 2

@@ -806,25 +806,33 @@ int accblas_trsv_host(accblas_handle_t handle, accblas_dtype ar,
     return ACCBLAS_OK;
 }
 
-// Development aid (not declared in accblas.h): accblas_trsv that also records
-// 16 phase timestamps per block row into `trace` (device pointer,
-// ceil(n/128)*16 long longs).  Used by tools/trsv_trace.py.
+#if defined(ACCBLAS_DEV_HOOKS)
+// Development aids, compiled only into libaccblas_b200_dev.so (build.py
+// build_dev; never into the product library).
+// accblas_trsv that also records phase timestamps per block row into `trace`
+// (device pointer, ceil(n/128) * 64 long longs: 64 slots per block row).
 int accblas_dev_trsv_trace(accblas_handle_t handle, int ar, int st, int uplo,
                            int diag, int64_t n, const void* A, int64_t lda,
                            void* x, int64_t incx, long long* trace,
                            accblas_stream_t stream)
 {
     ACCBLAS_ENTER(handle);
+    if (n < 0 || lda < n || incx < 1 || trace == nullptr ||
+        (n > 0 && (A == nullptr || x == nullptr))) {
+        accblas::set_error("trsv trace: bad argument");
+        return ACCBLAS_ERR_INVALID;
+    }
     return accblas::trsv_impl(h, ar, st, uplo, diag, n, A, lda, x, incx, s,
                               trace);
 }
 
-// Development aid: per-CTA start/end timestamps of the next GEMV launches
-// (3 x grid unsigned long longs, device pointer; nullptr switches it off).
+// per-CTA start/end timestamps of the next GEMV launches (3 x grid unsigned
+// long longs, device pointer; nullptr switches it off)
 int accblas_dev_gemv_trace(unsigned long long* trace)
 {
     return accblas::set_gemv_trace(trace);
 }
+#endif  // ACCBLAS_DEV_HOOKS
 
 // Development knob (not part of the drop-in surface): set a launch-shape
 // parameter by name.  Unknown keys and out-of-range values are rejected.
@@ -853,6 +861,7 @@ int accblas_tune(const char* key, int value)
         {"gemv_stages", &Tuning::gemv_stages, 0, 4},
         {"gemv_rows8", &Tuning::gemv_rows8, 0, 1},
         {"trsv_variant", &Tuning::trsv_variant, 0, 1},
+        {"trsv_push", &Tuning::trsv_push, 0, 2},
         {"trsv_whole_block_spin", &Tuning::trsv_whole_block_spin, 0, 1},
         {"trsv_l2_ahead", &Tuning::trsv_l2_ahead, 0, 1 << 20},
         {"fill_generic", &Tuning::fill_generic, 0, 1},

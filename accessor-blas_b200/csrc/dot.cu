@@ -482,13 +482,15 @@ int launch_shape(Handle* h, std::int64_t n, const void* x, const void* y,
     const Tuning& t = tuning();
     int unroll = t.dot_unroll;
     int block = t.dot_block;
+    // same-box sweep on B200 (tools/sweep_dot_fill.py, profiles/r02_sweep.txt):
+    // four vectors of each operand in flight win or tie for every pair
+    // (fp16 storage: +5 % over two); 1024-thread CTAs are worth +3 % for
+    // Acc<fp64,fp64> and cost the other pairs 1-7 %
     if (unroll == 0) {
-        // same-box sweeps (tools/tune.py dot): 8-byte elements and halves like
-        // two vectors per operand in flight, fp32 storage four
-        unroll = sizeof(St) == 4 ? 4 : 2;
+        unroll = 4;
     }
     if (block == 0) {
-        block = 256;
+        block = (sizeof(St) == 8 && sizeof(Ar) == 8) ? 1024 : 256;
     }
     const int cps = t.dot_ctas_per_sm;
 #define ACCBLAS_DOT_SHAPE(B, U)                                               \

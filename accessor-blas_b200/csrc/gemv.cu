@@ -38,8 +38,10 @@
 
 namespace accblas {
 
-// development aid: when non-null, every CTA of gemv_stream_kernel records its
-// start / end time (globaltimer ns) and SM id at [3*blockIdx.x ...]
+#if defined(ACCBLAS_DEV_HOOKS)
+// development aid (libaccblas_b200_dev.so only): when non-null, every CTA of
+// gemv_stream_kernel records its start / end time (globaltimer ns) and SM id
+// at [3*blockIdx.x ...]
 __device__ unsigned long long* g_gemv_trace = nullptr;
 
 int set_gemv_trace(unsigned long long* ptr)
@@ -47,6 +49,7 @@ int set_gemv_trace(unsigned long long* ptr)
     ACCBLAS_CUDA(cudaMemcpyToSymbol(g_gemv_trace, &ptr, sizeof(ptr)));
     return ACCBLAS_OK;
 }
+#endif
 
 namespace {
 
@@ -681,7 +684,11 @@ void gemv_stream_kernel(
         PIPE >= 2 ? static_cast<unsigned>(__cvta_generic_to_shared(gemv_ring)) +
                         warp * (PIPE * (ROWS + 1) * 512) + lane * 16
                   : 0u;
+#if defined(ACCBLAS_DEV_HOOKS)
     unsigned long long* const trace = g_gemv_trace;
+#else
+    constexpr unsigned long long* trace = nullptr;
+#endif
     if (trace != nullptr && threadIdx.x == 0) {
         unsigned smid;
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));

@@ -163,16 +163,31 @@ def min_of_10(fn, torch):
 # ---------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle's port on the host cores
 # ---------------------------------------------------------------------------
-def cpu_gemv_run(steps, warmup, budget_s=25.0):
-    """Times the CPU port on the SAME workload (full 16384^2 GEMV,
+def host_threads():
+    """Host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to
+    its workers; the CPU arm sets its thread count explicitly instead."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_gemv_run(steps, warmup, budget_s=25.0, slabs=1):
+    """Times the CPU port on the SAME workload (GEMV of `slabs` 16384 x 16384
+    slabs = the row-sharded matrix the accblas arm spreads over `slabs` GPUs,
     Acc<fp64,fp32>, all host threads).  The only place bench.py executes
     anything under oracle/."""
     import numpy as np
     sys.path.insert(0, str(ROOT / "tests"))
     from oracle_binding import Oracle
     orc = Oracle()
-    m = n = M
-    A = orc.uniform(m * n, seed=42).astype(np.float32)
+    threads = host_threads()
+    orc.L.oracle_set_num_threads(threads)
+    n = N_COLS
+    m = M * slabs
+    A = np.empty(m * n, dtype=np.float32)
+    for sl in range(slabs):       # slab by slab: the fp64 draws are 2 GiB each
+        A[sl * M * n:(sl + 1) * M * n] = orc.uniform(M * n, seed=42, first_draw=sl * M * n)
     x = orc.uniform(n, seed=42, first_draw=m * n).astype(np.float32)
     y = orc.uniform(m, seed=42, first_draw=m * n + n).astype(np.float32)
     for _ in range(max(1, min(warmup, 2))):
@@ -186,31 +201,33 @@ def cpu_gemv_run(steps, warmup, budget_s=25.0):
         if time.perf_counter() - t_begin > budget_s:
             break
     ms = 1e3 * sum(times) / len(times)
-    gbs = gemv_bytes(m, n, 4) / (ms * 1e-3) / 1e9
+    total_bytes = slabs * gemv_bytes(M, n, 4)
+    gbs = total_bytes / (ms * 1e-3) / 1e9
     return {"value": gbs, "unit": "GB/s", "cores": orc.num_threads, "kind": "port",
             "sample": f"full workload (GEMV {m}x{n} Acc<fp64,fp32>), {len(times)} passes, "
                       f"OpenMP over rows, {orc.num_threads} threads",
-            "ms_per_step": ms, "steps_timed": len(times)}
+            "ms_per_step": ms, "steps_timed": len(times), "total_bytes": total_bytes}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_gemv_run(args.steps, args.warmup, budget_s=120.0)
+    world = max(1, args.gpus)
+    base = cpu_gemv_run(args.steps, args.warmup, budget_s=120.0, slabs=world)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "GB/s",
         "n_gpus": args.gpus, "steps": base["steps_timed"], "warmup": args.warmup,
         "ms_per_step": base["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(), "m": M, "n": N_COLS,
-                   "arithmetic": "fp64", "storage": "fp32"},
+        "config": workload_config(world, M, base["total_bytes"]),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "GB/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "the reference ships no CPU build of its kernels; this is the host port "
-                "of the accessor kernel bodies (oracle/cpu_baseline.cpp)",
+                "of the accessor kernel bodies (oracle/cpu_baseline.cpp) on the same "
+                f"{world} x (16384 x 16384) row slabs the accblas arm spreads over {world} GPU(s)",
     }
     print(json.dumps(line), flush=True)
 
@@ -218,6 +235,15 @@ def run_reference_arm(args):
 def workload_name():
     return ("configs[1]: GEMV m=n=16384, fp64 arithmetic on fp32 storage "
             "(Acc<fp64,fp32>), alpha=beta=1, uniform(-1,1) seed 42")
+
+
+def workload_config(world, rows_per_gpu, total_bytes):
+    """`config` of the JSON line: identical keys and values for both arms."""
+    return {"workload": workload_name(), "m_per_gpu": rows_per_gpu, "n": N_COLS,
+            "arithmetic": "fp64", "storage": "fp32",
+            "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+            "l2": "inputs exceed L2 (1 GiB matrix per GPU vs 126 MB L2)",
+            "algorithmic_bytes_per_step": total_bytes}
 
 
 # ---------------------------------------------------------------------------
@@ -235,6 +261,17 @@ def detail_pairs(ab, h, torch, peak):
         bl = capi.load_baselines()
     except Exception:
         bl = None
+    # the reference's OWN CUDA kernels on this GPU (oracle/_ref, compiled from
+    # /root/reference/cuda by oracle/Makefile): a labelled baseline row next to
+    # every pair, never part of the accblas path
+    refk = None
+    try:
+        sys.path.insert(0, str(ROOT / "tests"))
+        from oracle_binding import REF_LIB, RefKernels
+        if REF_LIB.exists():
+            refk = RefKernels()
+    except Exception:
+        refk = None
 
     # ---- GEMV 16384^2: fp64 master, converted on the device ----------------
     m = n = M
@@ -268,6 +305,16 @@ def detail_pairs(ab, h, torch, peak):
                 "frac_nominal_8TBps": gbs / NOMINAL_HBM_GBS,
                 "GFLOPps": (2 * m * n + 3 * m) / (ms * 1e-3) / 1e9,
                 "rel_error_vs_fp64_kernel": err}
+            if refk is not None:
+                y = y0.clone()
+                refk.gemv(ar, m, n, 1.0, A, n, x, 1, 1.0, y, 1)
+                refk.sync()
+                err = h.l1_error(m, ref, 1, y, 1)
+                ms = min_of_10(lambda: refk.gemv(ar, m, n, 1.0, A, n, x, 1, 0.0, y, 1), torch)
+                gbs = gemv_bytes(m, n, size[st]) / (ms * 1e-3) / 1e9
+                gemv[f"reference kernel Acc<{name[ar]},{name[st]}>"] = {
+                    "ms": ms, "GBps": gbs, "frac_measured_peak": gbs / peak,
+                    "rel_error_vs_fp64_kernel": err}
         if bl is not None and st != torch.float16:
             y = y0.clone()
             code = 0 if st == torch.float64 else 1
@@ -319,6 +366,15 @@ def detail_pairs(ab, h, torch, peak):
                 "frac_nominal_8TBps": gbs / NOMINAL_HBM_GBS,
                 "GFLOPps": 2 * nd / (ms * 1e-3) / 1e9,
                 "rel_error_vs_fp64_kernel": abs(got - ref_v) / abs(ref_v)}
+            if refk is not None:
+                refk.dot(ar, nd, x, 1, y, 1, res)
+                refk.sync()
+                got = float(res.item())
+                ms = min_of_10(lambda: refk.dot(ar, nd, x, 1, y, 1, res), torch)
+                gbs = dot_bytes(nd, size[st], size[res_t]) / (ms * 1e-3) / 1e9
+                dot[f"reference kernel Acc<{name[ar]},{name[st]}>"] = {
+                    "ms": ms, "GBps": gbs, "frac_measured_peak": gbs / peak,
+                    "rel_error_vs_fp64_kernel": abs(got - ref_v) / abs(ref_v)}
         if bl is not None and st != torch.float16:
             code = 0 if st == torch.float64 else 1
             res = torch.zeros(1, dtype=st, device=dev)
@@ -337,52 +393,85 @@ def detail_pairs(ab, h, torch, peak):
     del x64, y64
     torch.cuda.empty_cache()
 
-    # ---- TRSV n = 16384, lower: L of a pivoted LU (unit), U^T (non-unit) -------
+    # ---- TRSV n = 16384 on the pivoted LU of the uniform(-1,1) fixture ----------
+    # Row-major LU = [L \\ U]: lower/unit = L (BASELINE configs[3]).  Its
+    # transpose has the layout the reference's fixture has after cuSOLVER's
+    # column-major getrf (cuda/trsv_memory.cuh:131-168): upper/unit = L^T, the
+    # reference driver's default (cuda/trsv_benchmark.cu:26-27), and
+    # lower/non-unit = U^T, conditioned like the random matrix itself.
     nt = 16384
     g = torch.empty(nt * nt, dtype=torch.float64, device=dev)
     h.fill_uniform(nt, nt, g, nt, 42, 0)
     LU, _ = torch.linalg.lu_factor(g.view(nt, nt))
     del g
-    Lrow = LU.contiguous().view(-1)          # row-major: strict lower = L, upper = U
     b64 = torch.empty(nt, dtype=torch.float64, device=dev)
     h.fill_uniform(nt, 1, b64, 1, 42, nt * nt)
-    trsv = {}
-    xref = b64.clone()
-    h.trsv(torch.float64, ab.LOWER, ab.UNIT, nt, Lrow, nt, xref, 1)
-    A32 = torch.empty(nt * nt, dtype=torch.float32, device=dev)
     b32 = torch.empty(nt, dtype=torch.float32, device=dev)
-    h.convert(nt, nt, Lrow, nt, A32, nt)
     h.convert(nt, 1, b64, 1, b32, 1)
-    for label, ar, A, b in (("Acc<fp64,fp64>", torch.float64, Lrow, b64),
-                            ("Acc<fp64,fp32>", torch.float64, A32, b32),
-                            ("Acc<fp32,fp32>", torch.float32, A32, b32)):
-        xw = b.clone()
-        h.trsv(ar, ab.LOWER, ab.UNIT, nt, A, nt, xw, 1)
-        err = h.l1_error(nt, xref, 1, xw, 1)
-
-        def call():
-            xw.copy_(b)
-            h.trsv(ar, ab.LOWER, ab.UNIT, nt, A, nt, xw, 1)
-        ms_total = min_of_10(call, torch)
-        ms_copy = min_of_10(lambda: xw.copy_(b), torch)
-        ms = ms_total - ms_copy
-        s = A.element_size()
-        trsv[label] = {"ms": ms, "GBps": trsv_bytes(nt, s) / (ms * 1e-3) / 1e9,
-                       "rel_error_vs_fp64_kernel": err, "triangle": "lower, unit (L of LU)"}
-    if bl is not None:
-        for label, code, A, b in (("cuBLAS fp64", 0, Lrow, b64), ("cuBLAS fp32", 1, A32, b32)):
+    trsv_all = {}
+    cases = (("lower_unit", "lower, unit (L of LU)", False, ab.LOWER, ab.UNIT),
+             ("upper_unit", "upper, unit (L^T; the reference driver's default)", True,
+              ab.UPPER, ab.UNIT),
+             ("lower_nonunit", "lower, non-unit (U^T; ill-conditioned for every solver)", True,
+              ab.LOWER, ab.NON_UNIT))
+    for key, label, transposed, uplo, diag in cases:
+        M64 = (LU.t().contiguous() if transposed else LU.contiguous()).view(-1)
+        A32 = torch.empty(nt * nt, dtype=torch.float32, device=dev)
+        h.convert(nt, nt, M64, nt, A32, nt)
+        trsv = {}
+        xref = b64.clone()
+        h.trsv(torch.float64, uplo, diag, nt, M64, nt, xref, 1)
+        pairs = (("Acc<fp64,fp64>", torch.float64, M64, b64),
+                 ("Acc<fp64,fp32>", torch.float64, A32, b32),
+                 ("Acc<fp32,fp32>", torch.float32, A32, b32))
+        if key != "lower_unit":
+            pairs = pairs[1:2]
+        for plabel, ar, A, b in pairs:
             xw = b.clone()
-            bl.accblas_baseline_cublas_trsv(code, 0, 1, nt, A.data_ptr(), nt, xw.data_ptr(),
-                                            1, stream)
+            h.trsv(ar, uplo, diag, nt, A, nt, xw, 1)
             err = h.l1_error(nt, xref, 1, xw, 1)
 
             def call():
                 xw.copy_(b)
-                bl.accblas_baseline_cublas_trsv(code, 0, 1, nt, A.data_ptr(), nt,
-                                                xw.data_ptr(), 1, stream)
+                h.trsv(ar, uplo, diag, nt, A, nt, xw, 1)
             ms = min_of_10(call, torch) - min_of_10(lambda: xw.copy_(b), torch)
-            trsv[label] = {"ms": ms, "rel_error_vs_fp64_kernel": err}
-    out["trsv_16384_lower_unit"] = trsv
+            sz = A.element_size()
+            nbytes = trsv_bytes(nt, sz) - (nt * sz if diag == ab.UNIT else 0)
+            trsv[plabel] = {"ms": ms, "GBps": nbytes / (ms * 1e-3) / 1e9,
+                            "frac_measured_peak": nbytes / (ms * 1e-3) / 1e9 / peak,
+                            "rel_error_vs_fp64_kernel": err, "triangle": label}
+            if refk is not None:
+                xr = b.clone()
+                refk.trsv(ar, uplo == ab.UPPER, diag == ab.UNIT, nt, A, nt, xr, 1)
+                refk.sync()
+                err = h.l1_error(nt, xref, 1, xr, 1)
+
+                def rcall():
+                    xr.copy_(b)
+                    refk.trsv(ar, uplo == ab.UPPER, diag == ab.UNIT, nt, A, nt, xr, 1)
+                ms = min_of_10(rcall, torch) - min_of_10(lambda: xr.copy_(b), torch)
+                trsv[f"reference kernel {plabel}"] = {"ms": ms, "rel_error_vs_fp64_kernel": err}
+        if bl is not None:
+            cub = (("cuBLAS fp64", 0, M64, b64), ("cuBLAS fp32", 1, A32, b32))
+            for clabel, code, A, b in (cub if key == "lower_unit" else cub[:1]):
+                xw = b.clone()
+                upper = 1 if uplo == ab.UPPER else 0
+                unit = 1 if diag == ab.UNIT else 0
+                bl.accblas_baseline_cublas_trsv(code, upper, unit, nt, A.data_ptr(), nt,
+                                                xw.data_ptr(), 1, stream)
+                err = h.l1_error(nt, xref, 1, xw, 1)
+
+                def ccall():
+                    xw.copy_(b)
+                    bl.accblas_baseline_cublas_trsv(code, upper, unit, nt, A.data_ptr(), nt,
+                                                    xw.data_ptr(), 1, stream)
+                ms = min_of_10(ccall, torch) - min_of_10(lambda: xw.copy_(b), torch)
+                trsv[clabel] = {"ms": ms, "rel_error_vs_fp64_kernel": err}
+        trsv_all[key] = trsv
+        del M64, A32
+    out["trsv_16384_lower_unit"] = trsv_all["lower_unit"]
+    out["trsv_16384_upper_unit"] = trsv_all["upper_unit"]
+    out["trsv_16384_lower_nonunit"] = trsv_all["lower_nonunit"]
     return out
 
 
@@ -524,14 +613,55 @@ def run_accblas_arm(args):
         "ms_per_step_nccl_allreduce": nccl_ms,
         "result": float(sdot(xd, yd, torch.float32).item())}
     del xd, yd
+    torch.cuda.empty_cache()
+
+    # -- e2e with the matrix RESIDENT: how the reference's drivers (and an
+    #    iterative solver) run -- the matrix is uploaded once, every step moves
+    #    x in and y out through pinned host memory around one GEMV
+    #    (cuda/utils.cuh:236-262 times only the launch)
+    y_res = y.clone()
+
+    def e2e_resident_step():
+        x.copy_(x_h, non_blocking=True)
+        gemv(1.0, A, x, 1.0, y_res)
+        y_h.copy_(y_res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    res_steps = max(10, min(args.steps, 100))
+    for _ in range(3):
+        e2e_resident_step()
+    if barrier:
+        barrier()
+    t0 = time.perf_counter()
+    for _ in range(res_steps):
+        e2e_resident_step()
+    res_ms = (time.perf_counter() - t0) * 1e3 / res_steps
+    if world > 1:
+        t = torch.tensor([res_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res_ms = float(t.item())
+    extra["e2e_resident"] = {
+        "what": "matrix uploaded once; per step x H2D + GEMV + y D2H through pinned host "
+                "memory, host-synchronised (wall clock)",
+        "value": total_bytes / (res_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": res_ms,
+        "h2d_bytes_per_step": n * s, "d2h_bytes_per_step": rows * s}
+    del y_res
+
+    # -- BASELINE configs[4] (the multi-GPU row): strong scaling of a FIXED
+    #    64 GiB GEMV and a 2^32 DOT with its exchange, at every N
+    if not args.no_config5:
+        del A, A_h, A_np
+        A = A_h = A_np = None
+        torch.cuda.empty_cache()
+        extra["config5"] = config5_numbers(args, sharded, h, torch, dist, world, rank, dev,
+                                           barrier, peak)
 
     detail = None
     cpu = None
     if rank == 0 and world == 1:
-        del A_h, A_np
+        A = A_h = A_np = None
+        torch.cuda.empty_cache()
         if not args.no_detail:
-            del A
-            torch.cuda.empty_cache()
             detail = detail_pairs(ab, h, torch, peak)
         cpu = cpu_gemv_run(steps=8, warmup=1, budget_s=20.0)
 
@@ -548,11 +678,7 @@ def run_accblas_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(), "m_per_gpu": rows, "n": n,
-                       "arithmetic": "fp64", "storage": "fp32",
-                       "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
-                       "l2": "inputs exceed L2 (1 GiB matrix per GPU vs 126 MB L2)",
-                       "algorithmic_bytes_per_step": total_bytes},
+            "config": workload_config(world, rows, total_bytes),
             "roofline": {"bound": "hbm", "achieved": kernel_gbs, "peak": peak, "unit": "GB/s",
                          "frac": kernel_gbs / peak, "traffic": traffic,
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
@@ -575,11 +701,12 @@ def run_accblas_arm(args):
         dist.destroy_process_group()
 
 
-def run_config5(args, ab, sharded, h, torch, dist, world, rank, dev, barrier, peak):
+def config5_numbers(args, sharded, h, torch, dist, world, rank, dev, barrier, peak):
     """BASELINE.json configs[4]: FIXED total problem, sharded over the ranks
     (strong scaling): GEMV m = n = 131072 fp32 storage (64 GiB) row-sharded with
-    x broadcast once, and DOT n = 2^32 fp32 range-sharded with one 1-element
-    NCCL all-reduce per call.  Acc<fp64, fp32>."""
+    x broadcast once, and DOT n = 2^32 fp32 range-sharded with the partials
+    combined inside the kernel over peer memory (the 1-element NCCL all-reduce
+    is timed next to it).  Acc<fp64, fp32>.  Returns the numbers (all ranks)."""
     st, ar, s = torch.float32, torch.float64, 4
     m_total = n = 131072
     first, rows = sharded.row_partition(m_total, world, rank)
@@ -592,15 +719,28 @@ def run_config5(args, ab, sharded, h, torch, dist, world, rank, dev, barrier, pe
     sharded.broadcast_vector(x)
     h.fill_uniform(rows, 1, y, 1, 42, m_total * n + n + first)
     gemv = sharded.ShardedGemv(h, ar, m_total, n, n)
-    steps, warmup = min(args.steps, 20), min(args.warmup, 5)
-    ms = time_launches(lambda: gemv(1.0, A, x, 1.0, y), steps, warmup, torch, barrier)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    steps, warmup = min(args.steps, 20), max(3, min(args.warmup, 5))
+
+    def max_over_ranks(v):
+        if world > 1:
+            t = torch.tensor([v], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return v
+
+    ms = max_over_ranks(time_launches(lambda: gemv(1.0, A, x, 1.0, y), steps, warmup, torch,
+                                      barrier))
     gemv_total = gemv_bytes(m_total, n, s)
-    checksum = float(y.double().abs().sum().item())
-    del A
+    # checksum of this rank's slab of y after warmup + steps accumulating GEMVs
+    # is not comparable across N; a single GEMV into a fresh y is
+    y1 = torch.empty(rows, dtype=st, device=dev)
+    h.fill_uniform(rows, 1, y1, 1, 42, m_total * n + n + first)
+    gemv(1.0, A, x, 1.0, y1)
+    checksum = y1.double().sum()
+    if world > 1:
+        dist.all_reduce(checksum, op=dist.ReduceOp.SUM)
+    checksum = float(checksum.item())
+    del A, y1
     torch.cuda.empty_cache()
 
     nd = 2 ** 32
@@ -610,35 +750,54 @@ def run_config5(args, ab, sharded, h, torch, dist, world, rank, dev, barrier, pe
     h.fill_uniform(1, d_count, xd, d_count, 42, d_first)
     h.fill_uniform(1, d_count, yd, d_count, 42, nd + d_first)
     sdot = sharded.ShardedDot(h, ar, nd, fused=True)
-    dot_ms = time_launches(lambda: sdot(xd, yd, torch.float32), steps, warmup, torch, barrier)
-    if world > 1:
-        t = torch.tensor([dot_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dot_ms = float(t.item())
+    dot_ms = max_over_ranks(time_launches(lambda: sdot(xd, yd, torch.float32), steps, warmup,
+                                          torch, barrier))
     dot_value = float(sdot(xd, yd, torch.float64).item())
+    nccl_ms = None
+    if world > 1:
+        ndot = sharded.ShardedDot(h, ar, nd, fused=False)
+        nccl_ms = max_over_ranks(time_launches(lambda: ndot(xd, yd, torch.float32), steps,
+                                               warmup, torch, barrier))
+    del xd, yd
+    torch.cuda.empty_cache()
+    return {
+        "workload": "configs[4]: row-sharded GEMV m=n=131072 fp32 storage (64 GiB, FIXED total: "
+                    "strong scaling) + DOT n=2^32 range-sharded, Acc<fp64,fp32>",
+        "steps": steps, "warmup": warmup, "rows_per_gpu": rows,
+        "gemv": {"ms_per_step": ms, "GBps": gemv_total / (ms * 1e-3) / 1e9,
+                 "GBps_per_gpu": gemv_bytes(rows, n, s) / (ms * 1e-3) / 1e9,
+                 "frac_measured_peak_per_gpu": gemv_bytes(rows, n, s) / (ms * 1e-3) / 1e9 / peak,
+                 "collective": "none in the timed region (x broadcast once before it)",
+                 "sum_of_y_after_one_gemv": checksum},
+        "dot": {"n": nd, "ms_per_step": dot_ms,
+                "GBps": dot_bytes(nd, s, 4) / (dot_ms * 1e-3) / 1e9,
+                "ms_per_step_nccl_allreduce": nccl_ms,
+                "result": dot_value,
+                "collective": ("partials exchanged inside the kernel over peer memory (NVLink)"
+                               if sdot.fused else "1-element all_reduce(SUM) per call")
+                if world > 1 else "none (N=1)"},
+    }
+
+
+def run_config5(args, ab, sharded, h, torch, dist, world, rank, dev, barrier, peak):
+    """`--workload config5`: the config-5 numbers as the main line."""
+    c5 = config5_numbers(args, sharded, h, torch, dist, world, rank, dev, barrier, peak)
     if rank == 0:
+        g = c5["gemv"]
         print(json.dumps({
-            "metric": METRIC, "value": gemv_total / (ms * 1e-3) / 1e9, "unit": "GB/s",
-            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "metric": METRIC, "value": g["GBps"], "unit": "GB/s",
+            "n_gpus": world, "steps": c5["steps"], "warmup": c5["warmup"],
+            "ms_per_step": g["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[4]: row-sharded GEMV m=n=131072 fp32 storage "
-                                   "(64 GiB) + DOT n=2^32 with one NCCL all-reduce, "
-                                   "Acc<fp64,fp32>", "rows_per_gpu": rows,
+            "config": {"workload": c5["workload"], "rows_per_gpu": c5["rows_per_gpu"],
                        "l2": "inputs exceed L2"},
-            "roofline": {"bound": "hbm", "achieved": gemv_bytes(rows, n, s) / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "achieved": g["GBps_per_gpu"],
                          "peak": peak, "unit": "GB/s",
-                         "frac": gemv_bytes(rows, n, s) / (ms * 1e-3) / 1e9 / peak,
-                         "traffic": None},
-            "gpu_launches": steps * world,
-            "extra": {"gemv_abs_checksum_rank0_slab": checksum,
-                      "dot": {"n": nd, "ms_per_step": dot_ms,
-                              "GBps": dot_bytes(nd, s, 4) / (dot_ms * 1e-3) / 1e9,
-                              "result": dot_value,
-                              "collective": ("in-kernel exchange over peer memory"
-                                             if sdot.fused else
-                                             "1-element all_reduce(SUM) per call")
-                              if world > 1 else "none (N=1)"}},
+                         "frac": g["frac_measured_peak_per_gpu"], "traffic": None},
+            "gpu_launches": c5["steps"] * world,
+            "extra": {"gemv_sum_of_y_after_one_gemv": g["sum_of_y_after_one_gemv"],
+                      "dot": c5["dot"]},
         }), flush=True)
     if world > 1:
         dist.barrier()
@@ -656,6 +815,8 @@ def main():
                          "config5 = BASELINE configs[4] (fixed 64 GiB GEMV + 2^32 DOT, strong)")
     ap.add_argument("--no-detail", action="store_true",
                     help="skip the per-pair / cuBLAS / TRSV detail table")
+    ap.add_argument("--no-config5", action="store_true",
+                    help="skip the configs[4] strong-scaling numbers in `extra`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -1,10 +1,15 @@
-"""Per-phase timeline of the TRSV kernel (development tool; run under gpurun).
+"""Per-phase timeline of the cluster TRSV kernel (development tool; run under
+gpurun with the development library):
 
-Slots per block row k (SM cycles unless noted):
-  0 start | 1 diag tile in smem | 2 sub-blocks inverted | 3 last dependency:
-  A loads issued | 4 x block seen by the poller | 5 CTA released | 6 row sums
-  reduced | 7..10 sub-steps done | 12 globaltimer(ns) at the end |
-  13 globaltimer(ns) when the last x block was seen
+    python accessor-blas_b200/build.py --dev
+    ACCBLAS_LIB=accessor-blas_b200/libaccblas_b200_dev.so python tools/trsv_trace.py [n] [st] [ar]
+
+Slots per block row k (SM clock unless noted): 0 start | 1 diagonal tile in
+shared memory | 2 sub-blocks inverted, products formed | 3 panels left of the
+last one streamed | 4 last x sub-block consumed | 6 right-hand side complete |
+10 solved | 12 globaltimer (ns) at the end | 13 globaltimer when the last x
+sub-block had been consumed | 40..43 globaltimer when sub-block 0..3 was
+published.
 """
 import ctypes
 import sys
@@ -19,15 +24,15 @@ import accessor_blas_b200 as ab  # noqa: E402
 from accessor_blas_b200 import capi  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-if len(sys.argv) > 4:
-    ab.tune("trsv_l2_ahead", int(sys.argv[4]))
 st = {"f64": torch.float64, "f32": torch.float32, "f16": torch.float16}[
     sys.argv[2] if len(sys.argv) > 2 else "f32"]
 ar_code = {"f64": 0, "f32": 1}[sys.argv[3] if len(sys.argv) > 3 else "f64"]
+if len(sys.argv) > 4:
+    ab.tune("trsv_push", int(sys.argv[4]))
 dev = torch.device("cuda:0")
 h = ab.Handle(0)
 lib = capi.load()
-fn = lib.accblas_dev_trsv_trace
+fn = lib.accblas_dev_trsv_trace   # AttributeError: not the development library
 fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
@@ -51,48 +56,37 @@ for it in range(3):
             trace.data_ptr(), torch.cuda.current_stream().cuda_stream)
     e1.record()
     torch.cuda.synchronize()
-    assert rc == 0
+    assert rc == 0, capi.load().accblas_last_error()
     print(f"run {it}: {e0.elapsed_time(e1) * 1e3:.1f} us total")
 t = trace.cpu().numpy().reshape(nb, 64)
-names = ["load diag", "invert+products", "(wait) ->last panel", "last x seen", "last FMAs",
-         "reduce+group barrier"]
-for k in sorted(set([0, 1, 2, nb // 4, nb // 2, nb - 2, nb - 1])):
-    if k < 0 or k >= nb:
-        continue
-    d = np.diff(t[k, :7])
-    print(f"block {k:4d}: " + "  ".join(f"{nm}={int(v)}" for nm, v in zip(names, d)))
-for k in (nb // 2, nb - 1):
-    base = t[k, 4]
-    parts = []
-    for step in range(4):
-        b, r = (int(t[k, 16 + 4 * step + i] - base) for i in range(2))
-        parts.append(f"x{step}: begin +{b}, in smem +{r}")
-    print(f"block {k} (cycles after its last x arrived): tile FMAs done +{int(t[k, 5] - base)}; "
-          f"rhs complete +{int(t[k, 6] - base)}; y FMAs +{int(t[k, 35] - base)}; y reduced +{int(t[k, 36] - base)}; " +
-          "; ".join(parts) + f"; CTA done +{int(t[k, 10] - base)}")
+for k in sorted(set([0, 1, 2, 7, 8, 9, nb // 4, nb // 2, nb - 2, nb - 1])):
+    if 0 <= k < nb:
+        print(f"block {k:4d}: tile {t[k, 1] - t[k, 0]:6d}  invert+products {t[k, 2] - t[k, 1]:6d}  "
+              f"stream {t[k, 3] - t[k, 2]:8d}  wait+last panel {t[k, 4] - t[k, 3]:8d}  "
+              f"rhs {t[k, 6] - t[k, 4]:5d}  solve {t[k, 10] - t[k, 6]:5d}   (cycles)")
 ends = t[:, 12].astype(np.float64)
 seen = t[:, 13].astype(np.float64)
+pub = t[:, 40:44].astype(np.float64)
 step = np.diff(ends)
-print(f"end-to-end per block step (globaltimer ns): median {np.median(step):.0f}, "
-      f"mean {step.mean():.0f}, p10 {np.percentile(step, 10):.0f}, p90 {np.percentile(step, 90):.0f}")
-lat = seen[1:] - ends[:-1]
-print(f"publish(k-1 end) -> seen by k (ns): median {np.median(lat):.0f}, "
-      f"p10 {np.percentile(lat, 10):.0f}, p90 {np.percentile(lat, 90):.0f}")
-crit = (t[1:, 29] - t[1:, 4]).astype(np.float64)
-print(f"last x seen -> own last sub-block in smem (cycles): median {np.median(crit):.0f}")
-print(f"first block done at {(ends[0] - ends.min()):.0f} ns after the earliest end; "
-      f"chain length {(ends.max() - ends[0]) / 1e3:.1f} us")
-
-pub3 = t[:, 43].astype(np.float64)
-inside = pub3[1:] - seen[1:]
-hand = seen[1:] - pub3[:-1]
-print(f"globaltimer: last x seen -> own x3 stored (ns): mean {inside.mean():.0f} median {np.median(inside):.0f}")
-print(f"globaltimer: x3 stored by k-1 -> last x seen by k (ns): mean {hand.mean():.0f} median {np.median(hand):.0f} "
-      f"p10 {np.percentile(hand, 10):.0f} p90 {np.percentile(hand, 90):.0f}")
-print("hand-off by position (ns):", " ".join(f"{int(v)}" for v in hand[::8]))
+print(f"end-to-end per block step (ns): median {np.median(step):.0f} mean {step.mean():.0f} "
+      f"p10 {np.percentile(step, 10):.0f} p90 {np.percentile(step, 90):.0f}; chain {(ends.max() - ends[0]) / 1e3:.1f} us")
+hand = seen[1:] - pub[:-1, 3]
+inside = pub[1:, 3] - seen[1:]
+k = np.arange(1, nb)
+for name, sel in (("inside a cluster", k % 8 != 0), ("across clusters", k % 8 == 0)):
+    if sel.any():
+        print(f"hand-off {name} (x3 published by k-1 -> consumed by k, ns): median {np.median(hand[sel]):.0f} "
+              f"p10 {np.percentile(hand[sel], 10):.0f} p90 {np.percentile(hand[sel], 90):.0f}")
+print(f"inside a CTA (last x consumed -> own x3 published, ns): median {np.median(inside):.0f} "
+      f"p10 {np.percentile(inside, 10):.0f} p90 {np.percentile(inside, 90):.0f}")
+got = t[:, 44:48].astype(np.float64)
+lat = got[1:] - pub[:-1]
+for name, sel in (("inside a cluster", k % 8 != 0), ("across clusters", k % 8 == 0)):
+    if sel.any():
+        print(f"sub-block published by k-1 -> barrier passed by k, {name} (ns): median "
+              f"{np.median(lat[sel], axis=0)}  p90 {np.percentile(lat[sel], 90, axis=0)}")
+steps_by_rank = [np.median(step[(k % 8) == r]) for r in range(8)]
+print("median step (ns) by rank in the cluster:", " ".join(f"{v:.0f}" for v in steps_by_rank))
+links = np.diff(pub[1:], axis=1)
+print(f"chain links x0->x1->x2->x3 (ns): median {np.median(links, axis=0)}")
 print(f"timer granularity: {np.gcd.reduce(np.diff(np.unique(t[:, 13])).astype(np.int64))} ns")
-
-ph = t[nb - 1, 48:52].astype(np.float64) / max(nb - 1, 1)
-print(f"CTA {nb - 1}: fast-path blocks {int(t[nb - 1, 52])} of {nb - 1}")
-print(f"CTA {nb - 1}: cycles per block iteration: x wait+check {ph[0]:.0f}, loads issued + panel widened {ph[1]:.0f}, "
-      f"re-poll + first barrier {ph[2]:.0f}, FMAs {ph[3]:.0f}")

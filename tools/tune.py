@@ -41,7 +41,7 @@ if "dot" in which:
                 results[key] = round(gbs, 1)
                 print(key, f"{gbs:8.1f} GB/s", flush=True)
         del x, y
-    ab.tune("dot_unroll", 4)
+    ab.tune("dot_unroll", 0)
     ab.tune("dot_ctas_per_sm", 0)
 
 if "gemv" in which:
