@@ -66,9 +66,11 @@ class MatrixInfo(NamedTuple):
         return self.size[0] * self.size[1]
 
 
-def _stream_ptr(stream) -> int:
+def _stream_ptr(stream, device=None) -> int:
+    """cudaStream_t of `stream`; None = the current stream of `device` (the
+    handle's device, which need not be the current one)."""
     if stream is None:
-        stream = torch.cuda.current_stream()
+        stream = torch.cuda.current_stream(device)
     return int(stream.cuda_stream) if hasattr(stream, "cuda_stream") else int(stream)
 
 
@@ -88,7 +90,7 @@ class Handle:
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else -1
         capi.check(self._lib.accblas_create(ctypes.byref(self._h), int(device)))
-        self.device = device
+        self.device = int(device) if int(device) >= 0 else torch.cuda.current_device()
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -116,7 +118,7 @@ class Handle:
         capi.check(self._lib.accblas_gemv(
             self._h, dtype_code(ar), st, m, n, float(alpha), _dev_ptr(A), lda,
             _dev_ptr(x), incx, float(beta), _dev_ptr(y), incy,
-            _stream_ptr(stream)))
+            _stream_ptr(stream, self.device)))
 
     def dot(self, ar, n: int, x: torch.Tensor, incx: int, y: torch.Tensor,
             incy: int, result: torch.Tensor, stream=None) -> None:
@@ -124,7 +126,7 @@ class Handle:
         capi.check(self._lib.accblas_dot(
             self._h, dtype_code(ar), dtype_code(x.dtype),
             dtype_code(result.dtype), n, _dev_ptr(x), incx, _dev_ptr(y), incy,
-            _dev_ptr(result), _stream_ptr(stream)))
+            _dev_ptr(result), _stream_ptr(stream, self.device)))
 
     # ---- multi-GPU DOT with the all-reduce inside the kernel (peer memory)
     def peer_export(self) -> bytes:
@@ -150,32 +152,44 @@ class Handle:
         devs = (ctypes.c_int * world)(*devices)
         capi.check(self._lib.accblas_peer_connect_ptrs(self._h, world, rank, ptrs, devs))
 
+    def peer_disconnect(self) -> None:
+        capi.check(self._lib.accblas_peer_disconnect(self._h))
+
+    def peer_set_timeout(self, seconds: float) -> None:
+        capi.check(self._lib.accblas_peer_set_timeout(self._h, float(seconds)))
+
+    def peer_status(self) -> int:
+        """0, or the number of the dot_allreduce call that timed out."""
+        failed = ctypes.c_uint64(0)
+        self._lib.accblas_peer_status(self._h, ctypes.byref(failed))
+        return int(failed.value)
+
     def dot_allreduce(self, ar, n: int, x: torch.Tensor, incx: int, y: torch.Tensor,
                       incy: int, result: torch.Tensor, stream=None) -> None:
         assert x.dtype == y.dtype
         capi.check(self._lib.accblas_dot_allreduce(
             self._h, dtype_code(ar), dtype_code(x.dtype),
             dtype_code(result.dtype), n, _dev_ptr(x), incx, _dev_ptr(y), incy,
-            _dev_ptr(result), _stream_ptr(stream)))
+            _dev_ptr(result), _stream_ptr(stream, self.device)))
 
     def trsv(self, ar, uplo: int, diag: int, n: int, A: torch.Tensor, lda: int,
              x: torch.Tensor, incx: int, stream=None) -> None:
         assert x.dtype == A.dtype
         capi.check(self._lib.accblas_trsv(
             self._h, dtype_code(ar), dtype_code(A.dtype), uplo, diag, n,
-            _dev_ptr(A), lda, _dev_ptr(x), incx, _stream_ptr(stream)))
+            _dev_ptr(A), lda, _dev_ptr(x), incx, _stream_ptr(stream, self.device)))
 
     def convert(self, rows: int, cols: int, src: torch.Tensor, ld_in: int,
                 dst: torch.Tensor, ld_out: int, stream=None) -> None:
         capi.check(self._lib.accblas_convert(
             self._h, dtype_code(dst.dtype), dtype_code(src.dtype), rows, cols,
-            _dev_ptr(src), ld_in, _dev_ptr(dst), ld_out, _stream_ptr(stream)))
+            _dev_ptr(src), ld_in, _dev_ptr(dst), ld_out, _stream_ptr(stream, self.device)))
 
     def fill_uniform(self, rows: int, cols: int, out: torch.Tensor, ld: int,
                      seed: int = 42, first_draw: int = 0, stream=None) -> None:
         capi.check(self._lib.accblas_fill_uniform(
             self._h, dtype_code(out.dtype), rows, cols, _dev_ptr(out), ld,
-            seed, first_draw, _stream_ptr(stream)))
+            seed, first_draw, _stream_ptr(stream, self.device)))
 
     def l1_error(self, n: int, ref: torch.Tensor, inc_ref: int,
                  res: torch.Tensor, inc_res: int, stream=None) -> float:
@@ -184,7 +198,7 @@ class Handle:
         capi.check(self._lib.accblas_l1_error(
             self._h, dtype_code(ref.dtype), dtype_code(res.dtype), n,
             _dev_ptr(ref), inc_ref, _dev_ptr(res), inc_res, _dev_ptr(out),
-            _stream_ptr(stream)))
+            _stream_ptr(stream, self.device)))
         d, s = out.tolist()
         return d / s if s != 0.0 else float("inf") if d != 0.0 else 0.0
 
@@ -196,20 +210,20 @@ class Handle:
         capi.check(self._lib.accblas_gemv_host(
             self._h, dtype_code(ar), st, m, n, float(alpha), A.ctypes.data, lda,
             x.ctypes.data, incx, float(beta), y.ctypes.data, incy,
-            _stream_ptr(stream)))
+            _stream_ptr(stream, self.device)))
 
     def dot_host(self, ar, n: int, x: np.ndarray, incx: int, y: np.ndarray,
                  incy: int, result: np.ndarray, stream=None) -> None:
         capi.check(self._lib.accblas_dot_host(
             self._h, dtype_code(ar), dtype_code(x.dtype),
             dtype_code(result.dtype), n, x.ctypes.data, incx, y.ctypes.data,
-            incy, result.ctypes.data, _stream_ptr(stream)))
+            incy, result.ctypes.data, _stream_ptr(stream, self.device)))
 
     def trsv_host(self, ar, uplo: int, diag: int, n: int, A: np.ndarray,
                   lda: int, x: np.ndarray, incx: int, stream=None) -> None:
         capi.check(self._lib.accblas_trsv_host(
             self._h, dtype_code(ar), dtype_code(A.dtype), uplo, diag, n,
-            A.ctypes.data, lda, x.ctypes.data, incx, _stream_ptr(stream)))
+            A.ctypes.data, lda, x.ctypes.data, incx, _stream_ptr(stream, self.device)))
 
 
 _default_handles = {}

@@ -21,6 +21,7 @@ BASELINES_PATH = HERE / "libaccblas_baselines.so"
 F64, F32, F16 = 0, 1, 2
 UPPER, LOWER = 0, 1
 NON_UNIT, UNIT = 0, 1
+ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_ALLOC, ERR_DATA, ERR_PEER = 1, 2, 3, 4, 5, 6
 
 # every symbol include/accblas.h declares: (name, restype, argtypes)
 _P = c_void_p

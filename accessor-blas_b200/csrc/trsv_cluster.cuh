@@ -22,7 +22,11 @@
 //     trip and a CTA barrier (~1700 cycles measured in trsv.cu).  The
 //     receiver sleeps on four mbarriers, one per sub-block, and starts on the
 //     32 columns that have arrived; after the last sub-block only 8 FMAs per
-//     thread, two shuffle levels and the diagonal solve remain.
+//     thread, two shuffle levels and the diagonal solve remain.  The solution
+//     is pushed to the NEXT TWO block rows: the second one streams that panel
+//     like any other, but does not have to wait for it to come round through
+//     L2 (that detour -- a poll of the progress vector, a staged copy, a
+//     panel, the tail -- was a second critical path three block rows long).
 //   * Everything else of a block row -- the panels left of the last one -- is
 //     streamed GEMV-style by 16 independent warps: a warp owns 8 rows, a lane
 //     4 consecutive columns of a 128-column panel (16-byte L1-bypassing
@@ -55,6 +59,7 @@ using namespace trsv_detail;
 
 constexpr int kRing = 4;        // x blocks staged in shared memory
 constexpr int kLookAhead = 2;   // blocks staged ahead of the warp that asks
+constexpr int kTail = 2;        // blocks before this one received by push
 constexpr int kMaxCluster = 8;
 
 // ---------------------------------------------------------------------------
@@ -163,20 +168,6 @@ __device__ __forceinline__ void st_async(unsigned addr, float v, unsigned bar)
         "[%0], %1, [%2];" ::"r"(addr),
         "r"(__float_as_uint(v)), "r"(bar)
         : "memory");
-}
-
-// plain store into (another CTA's) shared memory
-__device__ __forceinline__ void st_cluster(unsigned addr, double v)
-{
-    asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(addr),
-                 "l"(__double_as_longlong(v))
-                 : "memory");
-}
-__device__ __forceinline__ void st_cluster(unsigned addr, float v)
-{
-    asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(addr),
-                 "r"(__float_as_uint(v))
-                 : "memory");
 }
 
 // ---------------------------------------------------------------------------
@@ -303,23 +294,70 @@ __device__ __forceinline__ Ar reduce_scatter_rows(const Ar (&v)[8], int lane)
     return w;
 }
 
+// Cold paths kept out of line: inlined eight times into the unrolled tail they
+// cost registers the hot path needs (ptxas spilled around them).
+// A quad that straddles the end of the matrix: element-wise.
+template <typename St>
+__device__ __noinline__ Quad<St> load_quad_edge(const St* p, int valid)
+{
+    return load_quad<St, 0>(p, valid);
+}
+// A block solved by ANOTHER cluster reaches this CTA through L2 only: one warp
+// polls the progress vector and delivers into this CTA's own push buffer with
+// the st.async a neighbour would have used.  Delivers the block's sub-blocks
+// in arrival order up to and including arrival `upto`; `next` = arrivals
+// delivered so far (returned updated).  ALL pending sub-blocks are polled in
+// the same round (their loads are in flight together), so consecutive
+// sub-blocks cost one L2 round trip between them only if they really are a
+// round trip apart -- polled one after the other, the last of the four was
+// delivered four round trips after the first became visible.
+template <typename Ar, bool UPPER>
+__device__ __noinline__ int deliver_from_l2(const Ar* xs_block, int valid,
+                                            int next, int upto,
+                                            unsigned dst_block,
+                                            unsigned bar_block, int lane)
+{
+    while (next <= upto) {
+        Ar v[kNSB];
+#pragma unroll
+        for (int u = 0; u < kNSB; ++u) {
+            const int idx = (UPPER ? kNSB - 1 - u : u) * kSB + lane;
+            v[u] = Ar{0};
+            if (u >= next && idx < valid) {
+                v[u] = ld_volatile(xs_block + idx);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kNSB; ++u) {
+            if (u == next &&
+                __all_sync(0xffffffffu, !Sentinel<Ar>::is(v[u]))) {
+                const int idx = (UPPER ? kNSB - 1 - u : u) * kSB + lane;
+                st_async(dst_block + idx * static_cast<unsigned>(sizeof(Ar)),
+                         v[u], bar_block + 8 * u);
+                ++next;
+            }
+        }
+    }
+    return next;
+}
+
 template <typename St, typename Ar, bool UPPER, bool UNIT, int VW, bool TRACE>
 __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
     std::int64_t n, const St* __restrict__ A, std::int64_t lda,
     St* __restrict__ x, std::int64_t incx, Ar* xs,
     unsigned* __restrict__ ticket, long long* __restrict__ trace_arg,
-    int l2_ahead, int push_mode)
+    int l2_ahead)
 {
     long long* const trace = TRACE ? trace_arg : nullptr;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ar* D = reinterpret_cast<Ar*>(smem_raw);  // kB x kLD
     Ar* ring = D + kB * kLD;                  // kRing x kB, staged x blocks
-    Ar* xpush = ring + kRing * kB;            // kB, the block solved last
-    Ar* rhs = xpush + kB;                     // kB
+    Ar* xpush = ring + kRing * kB;            // kTail x kB, the blocks solved last
+    Ar* rhs = xpush + kTail * kB;             // kB
     Ar* xsol = rhs + kB;                      // kB
     Ar* inv_diag = xsol + kB;                 // kB
     Ar* scratch = inv_diag + kB;              // kB, rehearsal right-hand side
-    __shared__ __align__(8) unsigned long long bars[2 * kRing + kNSB];
+    __shared__ __align__(8) unsigned long long bars[2 * kRing + kTail * kNSB];
     __shared__ unsigned ticket_s;
     __shared__ unsigned next_fetch;  // first x block nobody has claimed yet
 
@@ -339,12 +377,12 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
             mbar_init(bar_empty + 8 * s, kThreads / kWarp);
         }
 #pragma unroll
-        for (int t = 0; t < kNSB; ++t) {
+        for (int t = 0; t < kTail * kNSB; ++t) {
             mbar_init(bar_push + 8 * t, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
-        for (int t = 0; t < kNSB; ++t) {
+        for (int t = 0; t < kTail * kNSB; ++t) {
             // the one arrival; the phase completes when the 32 values are in
             mbar_arrive_expect_tx(bar_push + 8 * t,
                                   kSB * static_cast<unsigned>(sizeof(Ar)));
@@ -353,12 +391,6 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
         if (crank == 0) {
             ticket_s = atomicAdd(ticket, 1u);
         }
-    }
-    if (tid < kB) {
-        // push_mode 2: the pushed block is its own "has arrived" flag
-        Ar sentinel;
-        memset(&sentinel, 0xff, sizeof(Ar));
-        xpush[tid] = sentinel;
     }
     __syncthreads();
     cluster_sync_all();  // barriers armed and the ticket visible cluster-wide
@@ -379,9 +411,6 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
         const std::int64_t r0 = pb * kB;
         const int bs = static_cast<int>((n - r0 < kB) ? (n - r0) : kB);
         const std::int64_t deps = k;  // block rows solved before this one
-        // the block solved right before this one is delivered by the CTA of
-        // rank - 1 (same cluster), else fetched from the progress vector by warp 0
-        const bool pushed_by_neighbour = crank != 0;
 
         {
             const int trow = tid >> 2;  // row of the tile in the quad layout
@@ -491,14 +520,6 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
 
             const int mem_sub = trow >> 5;
             const int grp = UPPER ? kNSB - 1 - mem_sub : mem_sub;  // solve index
-            // where the solution of this block row is pushed to
-            const bool push_next =
-                crank + 1 < csize && k + 1 < nb;
-            const unsigned next_push =
-                map_to_rank(smem_addr(xpush), push_next ? crank + 1 : crank);
-            const unsigned next_bar =
-                map_to_rank(bar_push, push_next ? crank + 1 : crank);
-
             // streaming geometry
             constexpr int EPL = Span<St>::kElems;  // elements per lane and row
             constexpr int CW = kWarp * EPL;        // columns per chunk
@@ -507,29 +528,45 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
             // fp32 arithmetic: two accumulators per row, chains as short as
             // trsv.cu's
             constexpr int NA = std::is_same<Ar, float>::value ? 2 : 1;
-            const St* rowbase;
-            int rmax;  // rows past the end of the matrix re-read a valid row
-            {
-                std::int64_t rw = r0 + RW * warp;
-                const std::int64_t room = n - 1 - rw;
-                rmax = room >= RW - 1 ? RW - 1
-                                      : (room > 0 ? static_cast<int>(room) : 0);
-                rw = rw < n ? rw : n - 1;
-                rowbase = A + rw * lda + EPL * lane;
-            }
-            const int group_blocks =
-                l2_ahead > 0
-                    ? max(1, l2_ahead / (kB * static_cast<int>(sizeof(St))))
-                    : 0;
-
 #pragma unroll 1
             // (the first block row of the solve order has nobody to wait for:
             // no rehearsal)
             for (int pass = (k == 0 ? 1 : 0); pass < 2; ++pass) {
                 const bool real = pass == 1;
                 Ar* rhs_cur = real ? rhs : scratch;
-                const std::int64_t panels = (real && deps > 0) ? deps - 1 : 0;
+                // streamed panels: blocks 0 .. deps - 2 of the solve order.  The
+                // x of the last of them (the block solved two positions back)
+                // arrives by push, like the tail's; the others come through
+                // the ring from L2
+                const std::int64_t panels = real ? (deps > 1 ? deps - 1 : 0) : 0;
+                const std::int64_t ring_panels = panels > 0 ? panels - 1 : 0;
                 const std::int64_t items = panels * CPP;
+                // The streaming geometry is (re)computed inside the pass: kept
+                // outside, it stays live through the tail and the solve of
+                // BOTH passes, where registers are what the kernel is short
+                // of.  `zero` is opaque to the compiler, so nothing here can be
+                // hoisted out of the loop.
+                int zero = 0;
+                asm volatile("" : "+r"(zero));
+                const St* rowbase;
+                int rmax;  // rows past the end of the matrix re-read a valid row
+                {
+                    std::int64_t rw = r0 + RW * warp + zero;
+                    const std::int64_t room = n - 1 - rw;
+                    rmax = room >= RW - 1
+                               ? RW - 1
+                               : (room > 0 ? static_cast<int>(room) : 0);
+                    rw = rw < n ? rw : n - 1;
+                    rowbase = A + rw * lda + EPL * lane;
+                }
+                const std::int64_t tail_prefetch_at =
+                    panels > 6 ? panels - 6 : 0;
+                const unsigned self_push = map_to_rank(smem_addr(xpush), crank);
+                const unsigned self_bar = map_to_rank(bar_push, crank);
+                const int group_blocks =
+                    l2_ahead + zero > 0
+                        ? max(1, l2_ahead / (kB * static_cast<int>(sizeof(St))))
+                        : 0;
 
                 Ar acc[RW][NA];
 #pragma unroll
@@ -622,7 +659,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                 // make sure blocks up to `upto` are staged or being staged:
                 // claim (in order) whatever nobody has claimed yet
                 auto stage_ahead = [&](std::int64_t upto) {
-                    upto = upto < panels - 1 ? upto : panels - 1;
+                    upto = upto < ring_panels - 1 ? upto : ring_panels - 1;
                     for (;;) {
                         unsigned b = 0xffffffffu;  // nothing to do
                         if (lane == 0) {
@@ -648,16 +685,60 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                     const int c = static_cast<int>(it % CPP);
                     const int slot = static_cast<int>(jj % kRing);
                     if (c == 0) {
-                        stage_ahead(jj + kLookAhead);
-                        mbar_wait(bar_full + 8 * slot,
-                                  static_cast<unsigned>(jj / kRing) & 1u);
-                        if (group_blocks > 0 && jj % group_blocks == 0) {
-                            l2_prefetch_group(jj + group_blocks);
+                        if (jj == tail_prefetch_at) {
+                            // the tiles of the kTail blocks solved last are
+                            // read in the quad layout, two sub-blocks at a
+                            // time, with next to nothing in flight: they must
+                            // come out of L2, not out of DRAM
+                            const std::int64_t c_lo =
+                                (UPPER ? pb + 1 : pb - kTail) * kB;
+                            std::int64_t c_hi = c_lo + kTail * kB;
+                            c_hi = c_hi < n ? c_hi : n;
+                            constexpr int kLineElems =
+                                128 / static_cast<int>(sizeof(St));
+                            const int r = lane >> 2;
+                            const St* row_l2 = rowbase - EPL * lane +
+                                               (r < rmax ? r : rmax) * lda;
+                            for (std::int64_t cc =
+                                     (c_lo > 0 ? c_lo : 0) + (lane & 3) * kLineElems;
+                                 cc < c_hi; cc += 4 * kLineElems) {
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                                    row_l2 + cc));
+                            }
+                        }
+                        if (jj < ring_panels) {
+                            stage_ahead(jj + kLookAhead);
+                            mbar_wait(bar_full + 8 * slot,
+                                      static_cast<unsigned>(jj / kRing) & 1u);
+                            if (group_blocks > 0 && jj % group_blocks == 0) {
+                                l2_prefetch_group(jj + group_blocks);
+                            }
+                        } else {
+                            // the block solved two positions back: pushed by
+                            // the CTA of rank - 2 -- or, when that one lives in
+                            // another cluster, fetched from L2 by warp 0
+                            if (crank < 2u && warp == 0) {
+                                const std::int64_t pbl = UPPER ? pb + 2 : pb - 2;
+                                const std::int64_t room = n - pbl * kB;
+                                deliver_from_l2<Ar, UPPER>(
+                                    xs + pbl * kB,
+                                    room < kB ? static_cast<int>(room) : kB, 0,
+                                    kNSB - 1,
+                                    self_push + kB * static_cast<unsigned>(
+                                                         sizeof(Ar)),
+                                    self_bar + 8 * kNSB, lane);
+                            }
+#pragma unroll
+                            for (int t = 0; t < kNSB; ++t) {
+                                mbar_wait_cluster(bar_push + 8 * (kNSB + t), 0u);
+                            }
                         }
                     }
                     Ar xv[EPL];
                     {
-                        const Ar* xb = ring + slot * kB + c * CW + EPL * lane;
+                        const Ar* xb =
+                            (jj < ring_panels ? ring + slot * kB : xpush + kB) +
+                            c * CW + EPL * lane;
 #pragma unroll
                         for (int e = 0; e < EPL; e += 2) {
                             const Pair<Ar> p2 =
@@ -676,7 +757,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                                        acc[r][e % NA]);
                         }
                     }
-                    if (c == CPP - 1) {
+                    if (c == CPP - 1 && jj < ring_panels) {
                         // the slot may be refilled once all 16 warps are past it
                         __syncwarp();
                         if (lane == 0) {
@@ -685,7 +766,49 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                     }
                 };
 
-                // ---- panels left of the last one: register double buffer
+                // ---- the tile of the block solved LAST is read in the quad
+                //      layout, sub-block by sub-block as the pushes arrive.  A
+                //      thread's share of a 32-column sub-block is two quads; a
+                //      window of TWO sub-blocks is kept in registers (the whole
+                //      tile would be 32 / 64 registers for fp32 / fp64
+                //      storage), the slot a consumed sub-block frees is
+                //      refilled with the one that arrives two chain links
+                //      later.  The first two are requested while the last
+                //      streamed chunk is still being waited for: nothing of
+                //      this tile's latency may end up behind the arrival of x.
+                const bool has_tail = real && deps > 0;
+                Quad<St> wq[2][2];
+                // t-th sub-block (in arrival order) of the last block's tile
+                auto load_sub = [&](int t, Quad<St> (&dst)[2]) {
+                    const int sbm = UPPER ? kNSB - 1 - t : t;
+                    const std::int64_t pbl = UPPER ? pb + 1 : pb - 1;
+                    std::int64_t r = r0 + trow;
+                    r = (r < n) ? r : n - 1;
+                    const std::int64_t col = pbl * kB + 32 * sbm + kEPL * seg;
+                    const St* src = A + r * lda + col;
+                    if (col + 16 + kEPL <= n) {
+                        dst[0] = load_quad<St, VW>(src, kEPL);
+                        dst[1] = load_quad<St, VW>(src + 16, kEPL);
+                    } else {
+#pragma unroll
+                        for (int ii = 0; ii < 2; ++ii) {
+                            const std::int64_t left = n - (col + 16 * ii);
+                            const int valid =
+                                left >= kEPL
+                                    ? kEPL
+                                    : (left > 0 ? static_cast<int>(left) : 0);
+                            dst[ii] = load_quad_edge<St>(src + 16 * ii, valid);
+                        }
+                    }
+                };
+                auto load_tail_window = [&]() {
+                    if (has_tail) {
+                        load_sub(0, wq[0]);
+                        load_sub(1, wq[1]);
+                    }
+                };
+
+                // ---- streamed panels: register double buffer
                 {
                     Span<St> buf_a[RW];
                     Span<St> buf_b[RW];
@@ -694,16 +817,22 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                         if (group_blocks > 0) {
                             l2_prefetch_group(0);
                         }
+                    } else {
+                        load_tail_window();
                     }
 #pragma unroll 1
                     for (std::int64_t it = 0; it < items; it += 2) {
                         if (it + 1 < items) {
                             load_chunk(it + 1, buf_b);
+                        } else {
+                            load_tail_window();
                         }
                         consume(it, buf_a);
                         if (it + 1 < items) {
                             if (it + 2 < items) {
                                 load_chunk(it + 2, buf_a);
+                            } else {
+                                load_tail_window();
                             }
                             consume(it + 1, buf_b);
                         }
@@ -711,28 +840,6 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                 }
                 if (real) {
                     ACCBLAS_TRACE(3, clock64());
-                }
-
-                // ---- the panel of the block solved last, quad layout: its
-                //      tile is requested now, the streamed sums are folded
-                //      while it is in flight
-                const bool last_panel = real && deps > 0;
-                Quad<St> lq[8];
-                if (last_panel) {
-                    const std::int64_t pbl = UPPER ? nb - deps : deps - 1;
-                    std::int64_t r = r0 + trow;
-                    r = (r < n) ? r : n - 1;
-                    const St* rp = A + r * lda + pbl * kB + kEPL * seg;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const std::int64_t left =
-                            n - (pbl * kB + 16 * i + kEPL * seg);
-                        const int valid =
-                            left >= kEPL
-                                ? kEPL
-                                : (left > 0 ? static_cast<int>(left) : 0);
-                        lq[i] = load_quad<St, VW>(rp + 16 * i, valid);
-                    }
                 }
                 {
                     Ar v[RW];
@@ -749,109 +856,81 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                         rhs_cur[trow] -= streamed;
                     }
                 }
-                if (last_panel && !pushed_by_neighbour && warp == 0 &&
-                    push_mode == 0) {
-                    // first CTA of a cluster: its predecessor lives in another
-                    // cluster and publishes through L2 only; warp 0 polls the
-                    // progress vector sub-block by sub-block and delivers
-                    // with the same st.async the neighbour would have used
-                    const std::int64_t pbl = UPPER ? nb - deps : deps - 1;
-                    const unsigned self_push =
-                        map_to_rank(smem_addr(xpush), crank);
-                    const unsigned self_bar = map_to_rank(bar_push, crank);
-#pragma unroll 1
-                    for (int t = 0; t < kNSB; ++t) {
-                        const int sbm = UPPER ? kNSB - 1 - t : t;
-                        const int idx = sbm * kSB + lane;
-                        const std::int64_t gi = pbl * kB + idx;
-                        Ar v = Ar{0};
-                        if (gi < n) {
-                            do {
-                                v = ld_volatile(xs + gi);
-                            } while (Sentinel<Ar>::is(v));
-                        }
-                        st_async(self_push +
-                                     idx * static_cast<unsigned>(sizeof(Ar)),
-                                 v, self_bar + 8 * t);
-                    }
-                }
-                if (last_panel) {
-                    // The sub-blocks of x arrive ~one chain link apart.  Only
-                    // the quads that meet the LAST one are widened ahead of
-                    // time (they sit on the critical path); the others are
-                    // widened after their own wait, in the shadow of the next
-                    // one (keeping all 32 widened values live costs 64
-                    // registers the kernel does not have).
-                    constexpr int kLastSub = UPPER ? 0 : kNSB - 1;
-                    Ar cvl[2][kEPL];
-#pragma unroll
-                    for (int ii = 0; ii < 2; ++ii) {
-                        lq[2 * kLastSub + ii].pin();
-#pragma unroll
-                        for (int e = 0; e < kEPL; ++e) {
-                            cvl[ii][e] =
-                                lq[2 * kLastSub + ii].template get<Ar>(e);
-                            pin_register(cvl[ii][e]);
-                        }
-                    }
+                if (has_tail) {
                     Ar a0 = Ar{}, a1 = Ar{};
+                    int l2_next = 0;  // arrivals delivered by warp 0
+                    // (a run-time loop over PAIRS of arrivals, slot = parity:
+                    // fully unrolled, ptxas hoisted the address arithmetic of
+                    // all arrivals and spilled)
+#pragma unroll 1
+                    for (int g2 = 0; g2 < kNSB; g2 += 2) {
 #pragma unroll
-                    for (int t = 0; t < kNSB; ++t) {
-                        const int sbm = UPPER ? kNSB - 1 - t : t;
-                        if (push_mode == 0) {
-                            mbar_wait_cluster(bar_push + 8 * t, 0u);
-                        } else {
-                            // one warp watches the 32 entries; the other 15
-                            // sleep in a hardware barrier (no polling that
-                            // could get in the way of the incoming stores)
-                            if (warp == t) {
-                                const int idx = sbm * kSB + lane;
-                                if (pushed_by_neighbour) {
-                                    while (Sentinel<Ar>::is(
-                                        ld_volatile(xpush + idx))) {
+                        for (int slot = 0; slot < 2; ++slot) {
+                            const int t = g2 + slot;
+                            const int sbm = UPPER ? kNSB - 1 - t : t;
+                            // a predecessor outside this cluster publishes
+                            // through L2 only: warp 0 polls the progress vector
+                            // and delivers with the st.async a neighbour would
+                            // have used
+                            if (crank == 0 && warp == 0) {
+                                const std::int64_t pbl = UPPER ? pb + 1 : pb - 1;
+                                const std::int64_t room = n - pbl * kB;
+                                l2_next = deliver_from_l2<Ar, UPPER>(
+                                    xs + pbl * kB,
+                                    room < kB ? static_cast<int>(room) : kB,
+                                    l2_next, t, self_push, self_bar, lane);
+                            }
+                            // The very last sub-block is widened BEFORE the
+                            // wait (its conversions would sit on the critical
+                            // path); the others are widened after their own
+                            // wait, in the shadow of the next one.
+                            const bool ahead = t == kNSB - 1;
+                            Ar cv[2][kEPL];
+                            if (ahead) {
+#pragma unroll
+                                for (int ii = 0; ii < 2; ++ii) {
+                                    wq[slot][ii].pin();
+#pragma unroll
+                                    for (int e = 0; e < kEPL; ++e) {
+                                        cv[ii][e] =
+                                            wq[slot][ii].template get<Ar>(e);
+                                        pin_register(cv[ii][e]);
                                     }
-                                } else {
-                                    // first CTA of a cluster: its predecessor
-                                    // publishes through L2 only
-                                    const std::int64_t gi =
-                                        (UPPER ? nb - deps : deps - 1) * kB + idx;
-                                    Ar v = Ar{0};
-                                    if (gi < n) {
-                                        do {
-                                            v = ld_volatile(xs + gi);
-                                        } while (Sentinel<Ar>::is(v));
-                                    }
-                                    st_volatile(xpush + idx, v);
                                 }
                             }
-                            named_barrier_sync(8 + t, kThreads);
-                        }
-                        if (TRACE && trace != nullptr && tid == 0) {
-                            trace[k * 64 + 44 + t] =
-                                static_cast<long long>(globaltimer_ns());
-                        }
-                        const Ar* xb = xpush + kEPL * seg;
+                            mbar_wait_cluster(bar_push + 8 * t, 0u);
+                            if (TRACE && trace != nullptr && tid == 0) {
+                                trace[k * 64 + 44 + t] =
+                                    static_cast<long long>(globaltimer_ns());
+                            }
+                            const Ar* xb = xpush + kEPL * seg;
+                            if (!ahead) {
 #pragma unroll
-                        for (int ii = 0; ii < 2; ++ii) {
-                            const int i = 2 * sbm + ii;
-                            if (t + 1 < kNSB) {
-                                lq[i].pin();
+                                for (int ii = 0; ii < 2; ++ii) {
+                                    wq[slot][ii].pin();
+#pragma unroll
+                                    for (int e = 0; e < kEPL; ++e) {
+                                        cv[ii][e] =
+                                            wq[slot][ii].template get<Ar>(e);
+                                    }
+                                }
+                            }
+                            if (t + 2 < kNSB) {
+                                // the slot is free: the sub-block that arrives
+                                // two links later takes it
+                                load_sub(t + 2, wq[slot]);
                             }
 #pragma unroll
-                            for (int e = 0; e < kEPL; e += 2) {
-                                const Pair<Ar> p2 =
-                                    *reinterpret_cast<const Pair<Ar>*>(
-                                        xb + 16 * i + e);
-                                const Ar c0 =
-                                    (t + 1 < kNSB)
-                                        ? lq[i].template get<Ar>(e)
-                                        : cvl[ii][e];
-                                const Ar c1 =
-                                    (t + 1 < kNSB)
-                                        ? lq[i].template get<Ar>(e + 1)
-                                        : cvl[ii][e + 1];
-                                a0 = fma_ar(c0, p2.a, a0);
-                                a1 = fma_ar(c1, p2.b, a1);
+                            for (int ii = 0; ii < 2; ++ii) {
+                                const int i = 2 * sbm + ii;
+#pragma unroll
+                                for (int e = 0; e < kEPL; e += 2) {
+                                    const Pair<Ar> p2 =
+                                        *reinterpret_cast<const Pair<Ar>*>(
+                                            xb + 16 * i + e);
+                                    a0 = fma_ar(cv[ii][e], p2.a, a0);
+                                    a1 = fma_ar(cv[ii][e + 1], p2.b, a1);
+                                }
                             }
                         }
                     }
@@ -871,6 +950,20 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                     ACCBLAS_TRACE(6, clock64());
                 }
 
+                // where the solution of this row is pushed: this thread's slot
+                // in the push buffer of the next kTail CTAs of the cluster
+                bool push_to[kTail];
+                unsigned push_dst[kTail];
+                unsigned push_bar[kTail];
+#pragma unroll
+                for (int d = 1; d <= kTail; ++d) {
+                    push_to[d - 1] = crank + d < csize && k + d < nb;
+                    const unsigned target = push_to[d - 1] ? crank + d : crank;
+                    push_dst[d - 1] = map_to_rank(
+                        smem_addr(xpush + (d - 1) * kB + trow), target);
+                    push_bar[d - 1] = map_to_rank(
+                        bar_push + 8 * ((d - 1) * kNSB), target);
+                }
                 // ---- diagonal block (see trsv.cu): y_g = Inv_g rhs_g for all
                 //      groups at once, then x_g = y_g - sum_{t<g} M(g,t) x_t
                 {
@@ -898,23 +991,25 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                     for (int step = 0; step < kNSB; ++step) {
                         const int ms = UPPER ? kNSB - 1 - step : step;
                         if (grp == step) {
+                            if (TRACE && real && trace != nullptr && seg == 0 &&
+                                (trow & 31) == 0) {
+                                trace[k * 64 + 16 + 2 * step] = clock64();
+                            }
                             // round through storage: later rows see what the
                             // accessor re-reads
                             const St stored = to_st<St, Ar>(y - corr);
                             const Ar back = to_ar<Ar, St>(stored);
                             if (seg == 0) {
                                 xsol[trow] = back;
-                                if (real && push_next) {
-                                    // the next block row first: it is the one
-                                    // waiting
-                                    const unsigned dst =
-                                        next_push +
-                                        trow * static_cast<unsigned>(sizeof(Ar));
-                                    if (push_mode == 0) {
-                                        st_async(dst, back, next_bar + 8 * step);
-                                    } else {
-                                        st_cluster(dst,
-                                                   Sentinel<Ar>::clean(back));
+                                if (real) {
+                                    // the block rows that come next first:
+                                    // they are the ones waiting
+#pragma unroll
+                                    for (int d = 1; d <= kTail; ++d) {
+                                        if (push_to[d - 1]) {
+                                            st_async(push_dst[d - 1], back,
+                                                     push_bar[d - 1] + 8 * step);
+                                        }
                                     }
                                 }
                             }
@@ -934,6 +1029,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                                 (trow & 31) == 0) {
                                 trace[k * 64 + 40 + step] =
                                     static_cast<long long>(globaltimer_ns());
+                                trace[k * 64 + 17 + 2 * step] = clock64();
                             }
                         } else if (grp > step) {
                             const int c2 = ms * kSB + 2 * seg;
@@ -1000,7 +1096,7 @@ int launch_cluster(Handle* h, std::int64_t n, const St* A, std::int64_t lda,
                    long long* trace, cudaStream_t stream)
 {
     auto kernel = trsv_cluster_kernel<St, Ar, UPPER, UNIT, VW, TRACE>;
-    const size_t smem = sizeof(Ar) * (kB * kLD + (kRing + 5) * kB);
+    const size_t smem = sizeof(Ar) * (kB * kLD + (kRing + kTail + 4) * kB);
     // the opt-in and the cluster occupancy are per device (and instantiation)
     static int clusters_on[64] = {};  // 0 = not asked yet, -1 = none fit
     const int slot = (h->device >= 0 && h->device < 64) ? h->device : 0;
@@ -1053,8 +1149,7 @@ int launch_cluster(Handle* h, std::int64_t n, const St* A, std::int64_t lda,
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     ACCBLAS_CUDA(cudaLaunchKernelEx(&cfg, kernel, n, A, lda, x, incx, xs, ticket,
-                                    trace, tuning().trsv_l2_ahead,
-                                    tuning().trsv_push));
+                                    trace, tuning().trsv_l2_ahead));
     return ACCBLAS_OK;
 }
 

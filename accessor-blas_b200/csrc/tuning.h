@@ -23,7 +23,6 @@ struct Tuning {
     int gemv_stages = 0;       // 0 = register path, 2..4 = bulk-copy ring depth
     int gemv_rows8 = 0;        // Acc<fp64,fp16>: 8 rows per group (halves the x conversions per element)
     int trsv_variant = 0;      // 0 = cluster kernel (DSMEM hand-off), 1 = one CTA per block row through L2
-    int trsv_push = 2;         // cluster kernel, hand-off to the next CTA: 0 = st.async + mbarrier transaction count, 2 = plain DSMEM stores, one warp polls shared memory, hardware barrier for the rest
     int trsv_whole_block_spin = 1;  // TRSV variant 1: a caught-up CTA waits for a whole x block (1) or 32 entries at a time (0)
     int trsv_l2_ahead = 1024;  // TRSV: bytes per row of the groups of off-diagonal tiles requested into L2 one group ahead (0 = off)
     int fill_generic = 0;      // fill_uniform: 1 = per-row kernel with __ddiv_rn also for contiguous outputs (A/B check)

@@ -110,7 +110,8 @@ def connect_peers(handle, group=None) -> bool:
     gathered = [None] * world
     dist.all_gather_object(gathered, mine, group=group)
     handle.peer_connect_ipc(world, rank, b"".join(gathered))
-    dist.barrier(group=group)  # nobody publishes into a mailbox not yet mapped
+    # no barrier needed: the mailbox was zeroed when it was exported and connect
+    # does not touch it, so an entry a faster peer publishes right away stays
     return True
 
 
@@ -135,16 +136,24 @@ class ShardedDot:
             self.fused = False
 
     def __call__(self, x_local: torch.Tensor, y_local: torch.Tensor,
-                 res_dtype: torch.dtype, stream=None) -> torch.Tensor:
+                 res_dtype: torch.dtype, stream=None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Returns a one-element tensor of `res_dtype` holding the dot product
+        of the whole vectors.  The result is written to `out` if given, else
+        to a FRESH tensor -- never to a buffer a later call overwrites (a CG
+        step keeps alpha and beta alive across two calls)."""
+        if out is None:
+            out = torch.empty(1, dtype=res_dtype, device=x_local.device)
+        elif out.dtype != res_dtype or out.numel() != 1:
+            raise ValueError("out must be a one-element tensor of res_dtype")
         if self.fused:
-            if self._partial is None or self._partial.dtype != res_dtype:
-                self._partial = torch.zeros(1, dtype=res_dtype, device=x_local.device)
             self.handle.dot_allreduce(self.ar, self.count, x_local, 1, y_local, 1,
-                                      self._partial, stream)
-            return self._partial
+                                      out, stream)
+            return out
         if self._partial is None:
             self._partial = torch.zeros(1, dtype=self.ar, device=x_local.device)
         self.handle.dot(self.ar, self.count, x_local, 1, y_local, 1,
                         self._partial, stream)
         allreduce_partial(self._partial, self.group)
-        return self._partial.to(res_dtype)
+        out.copy_(self._partial)      # the cast to the result type, after the reduction
+        return out

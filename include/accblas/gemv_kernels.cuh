@@ -22,6 +22,7 @@
 
 #include <accessor/range.hpp>
 #include <accessor/reduced_row_major.hpp>
+#include <accessor/row_major.hpp>
 
 #include "kernel_utils.cuh"
 #include "utils.cuh"
@@ -137,6 +138,57 @@ void acc_gemv(
         x->get_const_storage(),
         matrix_info{{res.length(0), res.length(1)}, res->get_stride(0)}, beta,
         res->get_stored_data());
+}
+
+// Plain row_major ranges (no precision change): the same fast path with
+// arithmetic type == storage type -- "all other accessors work accordingly"
+// (README.md:19) without falling back to the one-block-per-row template.
+template <typename ValueType>
+void acc_gemv(ValueType alpha,
+              const gko::acc::range<gko::acc::row_major<const ValueType, 2>>& mtx,
+              const gko::acc::range<gko::acc::row_major<const ValueType, 2>>& x,
+              ValueType beta,
+              const gko::acc::range<gko::acc::row_major<ValueType, 2>>& res)
+{
+    gemv<ValueType>(
+        matrix_info{{mtx.length(0), mtx.length(1)}, mtx->get_stride()[0]},
+        alpha, mtx->get_stored_data(),
+        matrix_info{{x.length(0), x.length(1)}, x->get_stride()[0]},
+        x->get_stored_data(),
+        matrix_info{{res.length(0), res.length(1)}, res->get_stride()[0]}, beta,
+        res->get_stored_data());
+}
+
+// Any other accessor (scaled_reduced_row_major, block_col_major, user types):
+// the accessor-generic kernel template, launched as the reference launches it
+// (cuda/gemv_kernels.cuh:190-192).  (Constrained on "is a range" instead of
+// spelling range<Accessor> in the signature: explicit template arguments of
+// the pointer launchers, acc_gemv<double>(...), must not be substituted into
+// range<double>.)
+namespace accblas_detail {
+template <typename T>
+struct is_range : std::false_type {};
+template <typename Accessor>
+struct is_range<gko::acc::range<Accessor>> : std::true_type {};
+}  // namespace accblas_detail
+
+template <typename ArType, typename MtxRange, typename XRange,
+          typename ResRange,
+          typename = typename std::enable_if<
+              accblas_detail::is_range<MtxRange>::value &&
+              accblas_detail::is_range<XRange>::value &&
+              accblas_detail::is_range<ResRange>::value>::type>
+void acc_gemv(ArType alpha, const MtxRange& mtx, const XRange& x, ArType beta,
+              const ResRange& res)
+{
+    constexpr std::int64_t block_size = 512;
+    const auto rows = mtx.length(0);
+    if (rows == 0) {
+        return;
+    }
+    kernel::acc_gemv<block_size>
+        <<<static_cast<unsigned>(rows), block_size>>>(alpha, mtx, x, beta, res);
+    CUDA_CALL(cudaGetLastError());
 }
 
 

@@ -124,91 +124,94 @@ inline accblas_handle_t default_handle()
 }
 }  // namespace accblas_detail
 
-struct cuda_event {
-    cuda_event() { CUDA_CALL(cudaEventCreate(&ev_)); }
-    ~cuda_event() { cudaEventDestroy(ev_); }
-    cuda_event(const cuda_event&) = delete;
-    cuda_event& operator=(const cuda_event&) = delete;
-    void reset()
-    {
-        CUDA_CALL(cudaEventDestroy(ev_));
-        CUDA_CALL(cudaEventCreate(&ev_));
-    }
-    cudaEvent_t& get() { return ev_; }
+// ---------------------------------------------------------------------------
+// Host plumbing the drivers use by name: cublas_get_handle(),
+// cublas_set_device_ptr_mode(), benchmark_function().  Own implementation; only
+// the names, the argument meaning and the timing protocol are the reference's.
+// ---------------------------------------------------------------------------
+namespace accblas_detail {
 
-private:
-    cudaEvent_t ev_;
+// cuBLAS handle with scalar arguments read from the host by default
+struct cublas_handle_deleter {
+    void operator()(cublasContext* handle) const
+    {
+        if (handle != nullptr) {
+            cublasDestroy(handle);
+        }
+    }
 };
 
-// CUDA-event timer on the default stream
-class CudaTimer {
+// Two events on the default stream that live as long as the stopwatch.
+class stopwatch {
 public:
-    void start() { CUDA_CALL(cudaEventRecord(start_.get(), 0)); }
-    void stop()
+    stopwatch()
     {
-        CUDA_CALL(cudaEventRecord(end_.get(), 0));
-        CUDA_CALL(cudaEventSynchronize(end_.get()));
+        CUDA_CALL(cudaEventCreate(&events_[0]));
+        CUDA_CALL(cudaEventCreate(&events_[1]));
     }
-    void reset()
+    ~stopwatch()
     {
-        start_.reset();
-        end_.reset();
+        cudaEventDestroy(events_[0]);
+        cudaEventDestroy(events_[1]);
     }
-    double get_time()
+    stopwatch(const stopwatch&) = delete;
+    stopwatch& operator=(const stopwatch&) = delete;
+
+    // milliseconds the default stream spent on `work`
+    template <typename Callable>
+    double time(Callable& work)
     {
-        float ms{};
-        CUDA_CALL(cudaEventElapsedTime(&ms, start_.get(), end_.get()));
-        return ms;
+        CUDA_CALL(cudaEventRecord(events_[0], nullptr));
+        work();
+        CUDA_CALL(cudaEventRecord(events_[1], nullptr));
+        CUDA_CALL(cudaEventSynchronize(events_[1]));
+        float elapsed_ms = 0.0f;
+        CUDA_CALL(cudaEventElapsedTime(&elapsed_ms, events_[0], events_[1]));
+        return static_cast<double>(elapsed_ms);
     }
 
 private:
-    cuda_event start_;
-    cuda_event end_;
+    cudaEvent_t events_[2];
 };
 
-using CublasContext = std::remove_pointer_t<cublasHandle_t>;
+}  // namespace accblas_detail
 
-inline std::unique_ptr<CublasContext, std::function<void(cublasHandle_t)>>
+inline std::unique_ptr<cublasContext, accblas_detail::cublas_handle_deleter>
 cublas_get_handle()
 {
-    cublasHandle_t handle;
-    CUBLAS_CALL(cublasCreate(&handle));
-    CUBLAS_CALL(cublasSetPointerMode(handle, CUBLAS_POINTER_MODE_HOST));
-    return {handle, [](cublasHandle_t h) { cublasDestroy(h); }};
+    cublasHandle_t raw = nullptr;
+    CUBLAS_CALL(cublasCreate(&raw));
+    std::unique_ptr<cublasContext, accblas_detail::cublas_handle_deleter> owner(
+        raw);
+    CUBLAS_CALL(cublasSetPointerMode(raw, CUBLAS_POINTER_MODE_HOST));
+    return owner;
 }
 
-inline void cublas_set_host_ptr_mode(cublasHandle_t handle)
-{
-    CUBLAS_CALL(cublasSetPointerMode(handle, CUBLAS_POINTER_MODE_HOST));
-}
-
+// scalar results / arguments live in device memory (DOT writes its result
+// there, cuda/dot_benchmark.cu:79)
 inline void cublas_set_device_ptr_mode(cublasHandle_t handle)
 {
     CUBLAS_CALL(cublasSetPointerMode(handle, CUBLAS_POINTER_MODE_DEVICE));
 }
 
 // The reference's timing protocol (cuda/utils.cuh:236-262): one warm-up call,
-// then ten single calls each bracketed by CUDA events; the MINIMUM in
-// milliseconds is reported.  skip == true: run once, return 0.
+// then ten single calls, each bracketed by CUDA events on the default stream;
+// the MINIMUM in milliseconds is what the drivers print.  skip == true (error
+// mode): run once so that the result exists, report 0.
 template <typename Callable>
 double benchmark_function(Callable func, bool skip = false)
 {
-    constexpr int bench_iters{10};
     func();
     synchronize();
     if (skip) {
-        return {};
+        return 0.0;
     }
-    CudaTimer timer;
-    double best = std::numeric_limits<double>::max();
-    for (int i = 0; i < bench_iters; ++i) {
-        timer.start();
-        func();
-        timer.stop();
-        best = std::min(best, timer.get_time());
-        timer.reset();
+    accblas_detail::stopwatch watch;
+    double fastest = std::numeric_limits<double>::infinity();
+    for (int repetition = 0; repetition < 10; ++repetition) {
+        fastest = std::min(fastest, watch.time(func));
     }
-    return best;
+    return fastest;
 }
 
 // Pairwise (halving) reduction of a strided single-column vector, in place

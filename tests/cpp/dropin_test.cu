@@ -6,12 +6,16 @@
 // returns 0, or prints the failing check and returns 1.
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <random>
 #include <vector>
 
+#include <accessor/block_col_major.hpp>
 #include <accessor/row_major.hpp>
+#include <accessor/scaled_reduced_row_major.hpp>
 
 #include <accblas/dot_kernels.cuh>
 #include <accblas/gemv_kernels.cuh>
@@ -150,6 +154,99 @@ int main()
             synchronize();
             const double e6 = l1_rel(want, to_host(dy, m));
             check(e6 < 1e-14, "kernel::acc_gemv<512> over row_major", e6, 0);
+            // the range launcher routes row_major to the C-ABI kernel
+            // (arithmetic == storage), bit-identical to gemv<double>
+            CUDA_CALL(cudaMemcpy(dy, y.data(), sizeof(double) * m,
+                                 cudaMemcpyHostToDevice));
+            gemv(m_info, 0.5, dA, x_info, dx, res_info, 2.0, dy);
+            synchronize();
+            const std::vector<double> fast = to_host(dy, m);
+            CUDA_CALL(cudaMemcpy(dy, y.data(), sizeof(double) * m,
+                                 cudaMemcpyHostToDevice));
+            acc_gemv(0.5, m_rm, x_rm, 2.0, res_rm);
+            synchronize();
+            const std::vector<double> routed = to_host(dy, m);
+            bool same = true;
+            for (size_type r = 0; r < m; ++r) {
+                same = same && routed[r] == fast[r];
+            }
+            check(same, "acc_gemv(row_major ranges) == gemv<double> bitwise", 0, 0);
+        }
+        // scaled_reduced_row_major: int16 storage with one fp64 scale per ROW,
+        // through the generic range launcher
+        {
+            std::vector<std::int16_t> Aq(m * stride);
+            std::vector<double> scale(m), want_q(m);
+            for (size_type r = 0; r < m; ++r) {
+                double big = 0;
+                for (size_type c = 0; c < n; ++c) {
+                    big = std::max(big, std::abs(A[r * stride + c]));
+                }
+                scale[r] = big / 32767.0;
+                double acc = 0;
+                for (size_type c = 0; c < n; ++c) {
+                    Aq[r * stride + c] = static_cast<std::int16_t>(
+                        std::lrint(A[r * stride + c] / scale[r]));
+                    acc += double(Aq[r * stride + c]) * scale[r] * x[c];
+                }
+                want_q[r] = 0.5 * acc + 2.0 * y[r];
+            }
+            std::int16_t* dq = to_device(Aq);
+            double* ds = to_device(scale);
+            CUDA_CALL(cudaMemcpy(dy, y.data(), sizeof(double) * m,
+                                 cudaMemcpyHostToDevice));
+            using sacc = gko::acc::scaled_reduced_row_major<2, double,
+                                                            const std::int16_t, 0b10>;
+            using rm = gko::acc::row_major<double, 2>;
+            auto m_s = gko::acc::range<sacc>(
+                m_info.size, static_cast<const std::int16_t*>(dq), ms,
+                static_cast<const double*>(ds));
+            auto x_p = gko::acc::range<typename rm::const_accessor>(
+                x_info.size, static_cast<const double*>(dx), xs);
+            auto r_p = gko::acc::range<rm>(res_info.size, dy, rs);
+            acc_gemv(0.5, m_s, x_p, 2.0, r_p);
+            synchronize();
+            const double e7 = l1_rel(want_q, to_host(dy, m));
+            check(e7 < 1e-14, "acc_gemv over scaled_reduced_row_major", e7, 0);
+            // writing through the proxy divides by the scale and rounds once
+            std::vector<double> probe{0.75 * scale[3] * 1000.0};
+            {
+                using wacc = gko::acc::scaled_reduced_row_major<2, double,
+                                                                std::int16_t, 0b10>;
+                std::vector<std::int16_t> hq(Aq);
+                std::vector<double> hs(scale);
+                auto w = gko::acc::range<wacc>(m_info.size, hq.data(), ms, hs.data());
+                w(3, 5) = probe[0];
+                check(hq[3 * stride + 5] == 750, "scaled proxy write", hq[3 * stride + 5], 750);
+                check(std::abs(double(w(3, 5)) - probe[0]) < 1e-12 * std::abs(probe[0]),
+                      "scaled proxy read back", double(w(3, 5)), probe[0]);
+            }
+            CUDA_CALL(cudaFree(dq));
+            CUDA_CALL(cudaFree(ds));
+        }
+        // block_col_major: the same matrix stored column-major
+        {
+            std::vector<double> At(n * m);
+            for (size_type r = 0; r < m; ++r) {
+                for (size_type c = 0; c < n; ++c) {
+                    At[c * m + r] = A[r * stride + c];
+                }
+            }
+            double* dt = to_device(At);
+            CUDA_CALL(cudaMemcpy(dy, y.data(), sizeof(double) * m,
+                                 cudaMemcpyHostToDevice));
+            using cm = gko::acc::block_col_major<const double, 2>;
+            using rm = gko::acc::row_major<double, 2>;
+            std::array<gko::acc::size_type, 1> cs{m};
+            auto m_c = gko::acc::range<cm>(m_info.size, static_cast<const double*>(dt), cs);
+            auto x_p = gko::acc::range<typename rm::const_accessor>(
+                x_info.size, static_cast<const double*>(dx), xs);
+            auto r_p = gko::acc::range<rm>(res_info.size, dy, rs);
+            acc_gemv(0.5, m_c, x_p, 2.0, r_p);
+            synchronize();
+            const double e8 = l1_rel(want, to_host(dy, m));
+            check(e8 < 1e-14, "acc_gemv over block_col_major", e8, 0);
+            CUDA_CALL(cudaFree(dt));
         }
         // plain kernel template
         CUDA_CALL(cudaMemcpy(dy, y.data(), sizeof(double) * m,

@@ -117,6 +117,31 @@ def run_gemv(handle, ar, A, m, n, lda, x, alpha, beta, y, incx=1, incy=1):
     return host(yd)
 
 
+@pytest.mark.parametrize("dst", ST)
+def test_fill_fast_equals_generic(ab, handle, dst):
+    """The streaming generator (constant-multiplier jumps, reciprocal-multiply
+    division) against the per-row kernel (__ddiv_rn) on 2^27 draws, several
+    starting points incl. beyond 2^32, bit for bit -- on the device."""
+    count = 2 ** 27
+    try:
+        for first in (0, 999_983, 2 ** 32 + 12345, 2 ** 40 + 1):
+            a = torch.empty(count, dtype=dst, device=DEV)
+            b = torch.empty(count, dtype=dst, device=DEV)
+            ab.tune("fill_generic", 0)
+            handle.fill_uniform(1, count, a, count, seed=42, first_draw=first)
+            ab.tune("fill_generic", 1)
+            handle.fill_uniform(1, count, b, count, seed=42, first_draw=first)
+            assert torch.equal(a.view(torch.uint8), b.view(torch.uint8)), first
+            # a ragged count and a matrix view take the same path
+            ab.tune("fill_generic", 0)
+            c = torch.empty(1000 * 777, dtype=dst, device=DEV)
+            handle.fill_uniform(1000, 777, c, 777, seed=42, first_draw=first)
+            assert torch.equal(c.view(torch.uint8), b[:1000 * 777].view(torch.uint8))
+            del a, b, c
+    finally:
+        ab.tune("fill_generic", 0)
+
+
 @pytest.mark.parametrize("ar", AR)
 @pytest.mark.parametrize("st", ST)
 @pytest.mark.parametrize("m,n,lda", [(1, 1, 1), (7, 3, 8), (100, 100, 100),
@@ -268,6 +293,84 @@ def test_dot_common_misalignment_is_peeled(oracle, handle, ar, st, off):
         handle.dot(ar, tiny, dev(x)[off:], 1, dev(y)[off:], 1, res)
         want = float(np.dot(x[off:off + tiny].astype(np.float64), y[off:off + tiny].astype(np.float64)))
         assert abs(float(res.item()) - want) <= 1e-6 * max(1.0, abs(want))
+
+
+@pytest.mark.parametrize("ar", AR)
+@pytest.mark.parametrize("st", ST)
+def test_dot_differently_misaligned_operands_keep_the_vector_path(oracle, handle, ar, st):
+    """x 16-byte aligned, y shifted by 1..7 elements: y's 16 bytes are fetched
+    in 8- / 4- / 2-byte pieces into the registers of the aligned kernel, so the
+    result must be BIT-identical to the same data with both operands aligned
+    (same launch shape, same summation order)."""
+    n = 1_000_003
+    x = stored(oracle, n, st, seed=41)
+    y = stored(oracle, n + 16, st, seed=43)
+    xd = dev(x)
+    per16 = 16 // np.dtype(NP[st]).itemsize
+    for shift in sorted({1, 2, 3, per16 // 2, per16 - 1} - {0}):
+        if shift >= per16:
+            continue
+        ys = y[shift:shift + n].copy()
+        aligned = torch.zeros(1, dtype=ar, device=DEV)
+        handle.dot(ar, n, xd, 1, dev(ys), 1, aligned)            # fresh, aligned copy
+        shifted = torch.zeros(1, dtype=ar, device=DEV)
+        ybuf = dev(y)
+        assert ybuf.data_ptr() % 16 == 0
+        handle.dot(ar, n, xd, 1, ybuf[shift:], 1, shifted)
+        swapped = torch.zeros(1, dtype=ar, device=DEV)
+        handle.dot(ar, n, ybuf[shift:], 1, xd, 1, swapped)        # the misaligned one first
+        exact = oracle.exact_dot(x, ys)
+        scale = float(np.abs(x.astype(np.float64) * ys.astype(np.float64)).sum())
+        assert torch.equal(aligned, shifted), (shift, aligned.item(), shifted.item())
+        assert abs(float(swapped.item()) - exact) <= DOT_TOL[ar] * scale
+        assert abs(float(shifted.item()) - exact) <= DOT_TOL[ar] * scale
+
+
+def test_dot_launch_shapes_and_integer_widening(oracle, ab, handle):
+    """Every CTA size / unroll the tuner can select, and the integer-pipe
+    widening of Acc<fp64,fp32> (bit-identical to the conversion-pipe path of
+    the same shape on ordinary data; Inf/NaN inputs take the exact fallback)."""
+    n = 3_000_017
+    try:
+        for ar, st in ((torch.float64, torch.float32), (torch.float32, torch.float16),
+                       (torch.float64, torch.float64)):
+            x = stored(oracle, n, st, seed=51)
+            y = stored(oracle, n, st, seed=52)
+            exact = oracle.exact_dot(x, y)
+            scale = float(np.abs(x.astype(np.float64) * y.astype(np.float64)).sum())
+            for block in (256, 512, 1024):
+                for unroll in (2, 4):
+                    ab.tune("dot_block", block)
+                    ab.tune("dot_unroll", unroll)
+                    outs = []
+                    for mix in ((0, 1) if (ar, st) == (torch.float64, torch.float32) else (0,)):
+                        ab.tune("dot_intmix", mix)
+                        res = torch.zeros(1, dtype=ar, device=DEV)
+                        handle.dot(ar, n, dev(x), 1, dev(y), 1, res)
+                        outs.append(res.clone())
+                        assert abs(float(res.item()) - exact) <= DOT_TOL[ar] * scale, (block, unroll, mix)
+                    if len(outs) == 2:
+                        assert torch.equal(outs[0], outs[1]), (block, unroll)
+        # non-finite inputs through the integer-widening path
+        ab.tune("dot_block", 0)
+        ab.tune("dot_unroll", 0)
+        x = stored(oracle, n, torch.float32, seed=53)
+        y = stored(oracle, n, torch.float32, seed=54)
+        for bad, where in ((np.inf, 12345), (-np.inf, n - 7), (np.nan, 2_000_000)):
+            xb = x.copy()
+            xb[where] = bad
+            got = []
+            for mix in (0, 1):
+                ab.tune("dot_intmix", mix)
+                res = torch.zeros(1, dtype=torch.float64, device=DEV)
+                handle.dot(torch.float64, n, dev(xb), 1, dev(y), 1, res)
+                got.append(float(res.item()))
+            assert (np.isnan(got[0]) and np.isnan(got[1])) or got[0] == got[1], (bad, got)
+            assert not np.isfinite(got[1])
+    finally:
+        ab.tune("dot_block", 0)
+        ab.tune("dot_unroll", 0)
+        ab.tune("dot_intmix", 0)
 
 
 @pytest.mark.parametrize("st", ST)
@@ -663,3 +766,42 @@ def test_gemv_fp16_fp64_fast_path_is_bit_identical_and_handles_non_finite(oracle
     keep = np.ones(m, dtype=bool)
     keep[[3, 7, 9]] = False
     assert np.array_equal(got2[keep], got[keep])
+
+
+# ---------------------------------------------------------------------------
+# programmatic dependent launch: producer -> consumer chains on one stream
+# ---------------------------------------------------------------------------
+def test_pdl_chains_match_serialised_launches(oracle, ab, handle):
+    """With PDL the next kernel's CTAs become resident while the previous
+    kernel still writes y; nothing it wrote may be read before
+    griddepcontrol.wait.  GEMV -> GEMV ping-pong (the output of one is the x of
+    the next, beta != 0 so y is read too) and GEMV -> DOT, 40 links each,
+    bit for bit against the same chain with PDL switched off."""
+    m = n = 4096 + 256
+    st, ar = torch.float32, torch.float64
+    A = dev(stored(oracle, m * n, st, seed=61) * np.float32(0.02))
+    v0 = dev(stored(oracle, n, st, seed=62))
+    w0 = dev(stored(oracle, n, st, seed=63))
+
+    def chain(pdl):
+        ab.tune("gemv_pdl", pdl)
+        ab.tune("dot_pdl", pdl)
+        v, w = v0.clone(), w0.clone()
+        dots = torch.zeros(40, dtype=torch.float64, device=DEV)
+        for i in range(40):
+            handle.gemv(ar, m, n, 1.0, A, n, v, 1, 0.5, w, 1)      # w = A v + w/2
+            handle.dot(ar, n, w, 1, v, 1, dots[i:i + 1])            # reads what GEMV just wrote
+            handle.gemv(ar, m, n, 1.0, A, n, w, 1, 0.25, v, 1)     # v = A w + v/4
+        torch.cuda.synchronize()
+        return v.clone(), w.clone(), dots.clone()
+
+    try:
+        ref = chain(0)
+        for _ in range(3):
+            got = chain(1)
+            for a, b in zip(ref, got):
+                assert torch.equal(a, b)
+        assert bool(torch.isfinite(ref[0]).all()) and float(ref[2].abs().max()) > 0
+    finally:
+        ab.tune("gemv_pdl", 1)
+        ab.tune("dot_pdl", 1)

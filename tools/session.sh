@@ -8,8 +8,8 @@ for step in "$@"; do
   case $step in
     trsvq)  timeout 300 python tools/trsv_check.py quick > gpurun_out/${tag}_trsv_check.log 2>&1; echo "trsv_check rc=$?" ;;
     trsv)   timeout 900 python tools/trsv_check.py > gpurun_out/${tag}_trsv_check.log 2>&1; echo "trsv_check rc=$?" ;;
-    trace)  for p in "f32 f64 2" "f32 f64 0" "f64 f64 2" "f32 f32 2"; do set -- $p
-              ACCBLAS_LIB=$PWD/accessor-blas_b200/libaccblas_b200_dev.so timeout 120 python tools/trsv_trace.py 16384 $1 $2 $3 > gpurun_out/${tag}_trace_$1_$2_push$3.log 2>&1; echo "trace $p rc=$?"; done ;;
+    trace)  for p in "f32 f64" "f64 f64" "f32 f32"; do set -- $p
+              ACCBLAS_LIB=$PWD/accessor-blas_b200/libaccblas_b200_dev.so timeout 120 python tools/trsv_trace.py 16384 $1 $2 > gpurun_out/${tag}_trace_$1_$2.log 2>&1; echo "trace $p rc=$?"; done ;;
     pytest) timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${tag}_pytest.log ;;
     pytestall) timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/${tag}_pytest.log ;;
     sweep)  timeout 600 python tools/sweep_dot_fill.py > gpurun_out/${tag}_sweep.log 2>&1; echo "sweep rc=$?" ;;

@@ -80,11 +80,7 @@ print(f"worst cluster/single error ratio: {worst:.3f}", flush=True)
 
 
 def timed(variant, ar, st, uplo, diag, n, T, lda, b):
-    # 0 = cluster kernel, st.async hand-off; 2 = cluster kernel, plain DSMEM
-    # stores + polling warp; 1 = one CTA per block row (L2 hand-off)
-    ab.tune("trsv_variant", 1 if variant == 1 else 0)
-    if variant != 1:
-        ab.tune("trsv_push", variant)
+    ab.tune("trsv_variant", variant)
     x = b.clone()
     best = 1e9
     for _ in range(8):
@@ -106,13 +102,12 @@ for n in ([4096, 16384] if quick else [1024, 4096, 16384, 32768]):
         T, b = fixture(n, n, st)
         for ar in (torch.float64, torch.float32):
             for uplo, diag in ((ab.LOWER, ab.UNIT), (ab.UPPER, ab.NON_UNIT)):
-                res = {0: 1e9, 1: 1e9, 2: 1e9}
+                res = {0: 1e9, 1: 1e9}
                 for rep in range(2):
-                    for variant in (0, 2, 1):
+                    for variant in (0, 1):
                         res[variant] = min(res[variant], timed(variant, ar, st, uplo, diag, n, T, n, b))
                 print(f"n={n:6d} Acc<{NAME[ar]},{NAME[st]}> {'lower' if uplo == ab.LOWER else 'upper'}/"
-                      f"{'unit' if diag == ab.UNIT else 'nonunit'}: cluster/st.async {res[0]:7.1f}  "
-                      f"cluster/poll {res[2]:7.1f}  single {res[1]:7.1f}  ({res[1] / res[2]:.2f}x)", flush=True)
+                      f"{'unit' if diag == ab.UNIT else 'nonunit'}: cluster {res[0]:7.1f}  single {res[1]:7.1f}  "
+                      f"({res[1] / res[0]:.2f}x)", flush=True)
         del T
 ab.tune("trsv_variant", 0)
-ab.tune("trsv_push", 2)

@@ -27,8 +27,6 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 st = {"f64": torch.float64, "f32": torch.float32, "f16": torch.float16}[
     sys.argv[2] if len(sys.argv) > 2 else "f32"]
 ar_code = {"f64": 0, "f32": 1}[sys.argv[3] if len(sys.argv) > 3 else "f64"]
-if len(sys.argv) > 4:
-    ab.tune("trsv_push", int(sys.argv[4]))
 dev = torch.device("cuda:0")
 h = ab.Handle(0)
 lib = capi.load()
@@ -87,6 +85,26 @@ for name, sel in (("inside a cluster", k % 8 != 0), ("across clusters", k % 8 ==
               f"{np.median(lat[sel], axis=0)}  p90 {np.percentile(lat[sel], 90, axis=0)}")
 steps_by_rank = [np.median(step[(k % 8) == r]) for r in range(8)]
 print("median step (ns) by rank in the cluster:", " ".join(f"{v:.0f}" for v in steps_by_rank))
+# one SM, one clock: last x consumed (slot 4) -> sub-block solutions published
+base = t[1:, 4].astype(np.float64)
+marks = []
+for st_ in range(4):
+    marks.append(np.median(t[1:, 16 + 2 * st_] - base))
+    marks.append(np.median(t[1:, 17 + 2 * st_] - base))
+print("cycles after the last x was consumed (median): rhs complete +%d; " % np.median(t[1:, 6] - base) +
+      "; ".join(f"x{i}: begin +{int(marks[2 * i])}, published +{int(marks[2 * i + 1])}" for i in range(4)) +
+      f"; all done +{int(np.median(t[1:, 10] - base))}")
+for kk in (33, 34, 35, 36):
+    if kk < nb:
+        b0 = t[kk, 0]
+        print(f"raw clock64 of block {kk} relative to its start: " +
+              " ".join(f"s{sl}={int(t[kk, sl] - b0)}" for sl in (1, 2, 3, 4, 6, 16, 17, 18, 19, 20, 21, 22, 23, 10)))
+        print(f"raw globaltimer of block {kk} relative to slot 13: " +
+              " ".join(f"s{sl}={int(t[kk, sl] - t[kk, 13])}" for sl in (44, 45, 46, 47, 13, 40, 41, 42, 43, 12)))
+dg = (t[1:, 12] - t[1:, 13]).astype(np.float64)
+dc = (t[1:, 10] - t[1:, 4]).astype(np.float64)
+print(f"same interval by both timers: clock64 {np.median(dc):.0f} cycles, globaltimer {np.median(dg):.0f} ns "
+      f"-> {np.median(dc) / max(np.median(dg), 1):.2f} GHz")
 links = np.diff(pub[1:], axis=1)
 print(f"chain links x0->x1->x2->x3 (ns): median {np.median(links, axis=0)}")
 print(f"timer granularity: {np.gcd.reduce(np.diff(np.unique(t[:, 13])).astype(np.int64))} ns")
