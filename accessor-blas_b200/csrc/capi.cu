@@ -847,9 +847,11 @@ int accblas_tune(const char* key, int value)
     static const Knob knobs[] = {
         {"dot_unroll", &Tuning::dot_unroll, 0, 4},
         {"dot_block", &Tuning::dot_block, 0, 1024},
-        {"dot_ctas_per_sm", &Tuning::dot_ctas_per_sm, 0, 32},
+        {"dot_ctas_per_sm", &Tuning::dot_ctas_per_sm, 0, 64},
         {"dot_pdl", &Tuning::dot_pdl, 0, 1},
         {"dot_intmix", &Tuning::dot_intmix, 0, 1},
+        {"dot_l1", &Tuning::dot_l1, 0, 1},
+        {"dot_waves", &Tuning::dot_waves, 0, 1},
         {"gemv_unroll", &Tuning::gemv_unroll, 0, 4},
         {"gemv_variant", &Tuning::gemv_variant, 0, 5},
         {"gemv_ctas_per_sm", &Tuning::gemv_ctas_per_sm, 0, 32},
@@ -859,8 +861,7 @@ int accblas_tune(const char* key, int value)
         {"gemv_force_pieces", &Tuning::gemv_force_pieces, -1, 8},
         {"gemv_taper", &Tuning::gemv_taper, 0, 1},
         {"gemv_stages", &Tuning::gemv_stages, 0, 4},
-        {"gemv_rows8", &Tuning::gemv_rows8, 0, 1},
-        {"trsv_variant", &Tuning::trsv_variant, 0, 1},
+        {"trsv_variant", &Tuning::trsv_variant, -1, 1},
         {"trsv_whole_block_spin", &Tuning::trsv_whole_block_spin, 0, 1},
         {"trsv_l2_ahead", &Tuning::trsv_l2_ahead, 0, 1 << 20},
         {"fill_generic", &Tuning::fill_generic, 0, 1},

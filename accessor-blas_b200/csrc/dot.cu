@@ -218,7 +218,8 @@ __device__ __forceinline__ void finish_dot(Ar local, Ar* partials,
 // Contiguous operands.  x is 16-byte aligned (after peeling `head` elements);
 // y is aligned to CBY bytes (16 = the same alignment as x).
 // MIX (fp32 storage, fp64 arithmetic only): x widened on the integer pipes.
-template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX>
+template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX,
+          bool L1ALLOC = false>
 __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     const St* __restrict__ x, const St* __restrict__ y, std::int64_t n,
     Ar* __restrict__ partials, unsigned* __restrict__ counter,
@@ -274,12 +275,15 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
         uint4 yr[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            xr[u] = ldg_stream_128(x + base + std::int64_t{u} * BLOCK * VEC);
+            xr[u] = L1ALLOC ? ldg_cached_128_ordered(
+                                  x + base + std::int64_t{u} * BLOCK * VEC)
+                            : ldg_stream_128(
+                                  x + base + std::int64_t{u} * BLOCK * VEC);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            yr[u] = ldg_pieces<CBY, true>(y + base +
-                                          std::int64_t{u} * BLOCK * VEC);
+            yr[u] = ldg_pieces<CBY, !L1ALLOC>(y + base +
+                                              std::int64_t{u} * BLOCK * VEC);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
@@ -416,14 +420,15 @@ __global__ __launch_bounds__(BLOCK) void dot_strided_kernel(
                           counter, result, res_dtype, scratch, px);
 }
 
-template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX>
+template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX,
+          bool L1ALLOC = false>
 int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
                   void* result, int res, int ctas_per_sm, cudaStream_t stream,
                   const PeerExchange& px, int head)
 {
     constexpr int VEC = vec_traits<St>::elems;
     constexpr std::int64_t TILE = std::int64_t{BLOCK} * VEC * UNROLL;
-    auto kernel = dot_stream_kernel<St, Ar, BLOCK, UNROLL, CBY, MIX>;
+    auto kernel = dot_stream_kernel<St, Ar, BLOCK, UNROLL, CBY, MIX, L1ALLOC>;
     // one resident wave: every CTA of the grid-stride loop is on the machine
     // from start to end (a partial second wave would leave a tail).  The
     // occupancy is a property of (instantiation, device).
@@ -439,7 +444,9 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
             resident_on[slot] = resident;
         }
     }
-    if (ctas_per_sm <= 0 || ctas_per_sm > resident) {
+    // (experiment `dot_waves`: more CTAs than are resident, i.e. several
+    // waves of shorter CTAs, the reference's launch shape)
+    if (ctas_per_sm <= 0 || (ctas_per_sm > resident && tuning().dot_waves == 0)) {
         ctas_per_sm = resident;
     }
     std::int64_t tiles = n / TILE;
@@ -474,7 +481,7 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
 
 // launch shape of the aligned kernel: CTA size and vectors in flight, from the
 // tuning knobs (0 = the per-pair default measured on B200)
-template <typename St, typename Ar, bool MIX>
+template <typename St, typename Ar, bool MIX, int CBY = 16>
 int launch_shape(Handle* h, std::int64_t n, const void* x, const void* y,
                  void* result, int res, cudaStream_t stream,
                  const PeerExchange& px, int head)
@@ -493,13 +500,28 @@ int launch_shape(Handle* h, std::int64_t n, const void* x, const void* y,
         block = (sizeof(St) == 8 && sizeof(Ar) == 8) ? 1024 : 256;
     }
     const int cps = t.dot_ctas_per_sm;
+    if constexpr (CBY == 16 && !MIX) {
+        // experiment `dot_l1`: the stream allocates in L1 (plain read-only
+        // loads, as the reference's scalar kernel issues them)
+        if (t.dot_l1 != 0 && unroll == 4) {
+            if (block == 1024) {
+                return launch_stream<St, Ar, 1024, 4, 16, false, true>(
+                    h, n, x, y, result, res, cps, stream, px, head);
+            }
+            return launch_stream<St, Ar, 256, 4, 16, false, true>(
+                h, n, x, y, result, res, cps, stream, px, head);
+        }
+    }
 #define ACCBLAS_DOT_SHAPE(B, U)                                               \
     if (block == B && unroll == U) {                                          \
-        return launch_stream<St, Ar, B, U, 16, MIX>(h, n, x, y, result, res,  \
-                                                    cps, stream, px, head);   \
+        return launch_stream<St, Ar, B, U, CBY, MIX>(h, n, x, y, result, res, \
+                                                     cps, stream, px, head);  \
     }
+    ACCBLAS_DOT_SHAPE(256, 1)
     ACCBLAS_DOT_SHAPE(256, 2)
     ACCBLAS_DOT_SHAPE(256, 4)
+    ACCBLAS_DOT_SHAPE(512, 1)
+    ACCBLAS_DOT_SHAPE(1024, 1)
     ACCBLAS_DOT_SHAPE(512, 2)
     ACCBLAS_DOT_SHAPE(512, 4)
     ACCBLAS_DOT_SHAPE(1024, 2)
@@ -543,22 +565,21 @@ int launch_dot(Handle* h, std::int64_t n, const void* x, std::int64_t incx,
                     return launch_shape<St, Ar, false>(h, rest, xp, yp, result,
                                                        res, stream, px, head);
                 }
-                // different misalignments: y in pieces of its own alignment
-                const int cps = tuning().dot_ctas_per_sm;
+                // different misalignments: y in pieces of its own alignment,
+                // same launch shape (hence the same bits) as the aligned call
                 if (dy % 8 == 0) {
-                    return launch_stream<St, Ar, 256, 4, 8, false>(
-                        h, rest, xp, yp, result, res, cps, stream, px, head);
+                    return launch_shape<St, Ar, false, 8>(h, rest, xp, yp, result,
+                                                          res, stream, px, head);
                 }
                 if constexpr (sizeof(St) <= 4) {
                     if (dy % 4 == 0) {
-                        return launch_stream<St, Ar, 256, 4, 4, false>(
-                            h, rest, xp, yp, result, res, cps, stream, px,
-                            head);
+                        return launch_shape<St, Ar, false, 4>(
+                            h, rest, xp, yp, result, res, stream, px, head);
                     }
                 }
                 if constexpr (sizeof(St) == 2) {
-                    return launch_stream<St, Ar, 256, 4, 2, false>(
-                        h, rest, xp, yp, result, res, cps, stream, px, head);
+                    return launch_shape<St, Ar, false, 2>(h, rest, xp, yp, result,
+                                                          res, stream, px, head);
                 }
             }
         }

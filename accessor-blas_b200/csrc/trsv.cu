@@ -758,7 +758,11 @@ int launch_trsv(Handle* h, int uplo, int diag, std::int64_t n, const void* A_v,
     }
     const bool upper = uplo == ACCBLAS_UPPER;
     const bool unit = diag == ACCBLAS_UNIT;
-    if (tuning().trsv_variant == 0) {
+    // which kernel: same-box A/B at n = 16384 (tools/trsv_check.py,
+    // profiles/r02_trsv_ab.txt) -- the cluster kernel is 12-24 % faster for fp16
+    // storage and 12-30 % slower for fp32 / fp64 storage
+    const int variant = tuning().trsv_variant;
+    if (variant == 0 || (variant < 0 && sizeof(St) == 2)) {
         constexpr int st_code =
             std::is_same<St, double>::value
                 ? ACCBLAS_F64

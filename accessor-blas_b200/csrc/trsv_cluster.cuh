@@ -294,14 +294,8 @@ __device__ __forceinline__ Ar reduce_scatter_rows(const Ar (&v)[8], int lane)
     return w;
 }
 
-// Cold paths kept out of line: inlined eight times into the unrolled tail they
-// cost registers the hot path needs (ptxas spilled around them).
-// A quad that straddles the end of the matrix: element-wise.
-template <typename St>
-__device__ __noinline__ Quad<St> load_quad_edge(const St* p, int valid)
-{
-    return load_quad<St, 0>(p, valid);
-}
+// Cold path kept out of line: inlined into the unrolled tail it costs registers
+// the hot path needs (ptxas spilled around it).
 // A block solved by ANOTHER cluster reaches this CTA through L2 only: one warp
 // polls the progress vector and delivers into this CTA's own push buffer with
 // the st.async a neighbour would have used.  Delivers the block's sub-blocks
@@ -616,35 +610,48 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(row_l2 + c));
                     }
                 };
-                // progress vector -> ring slot of block b (one warp)
-                auto fetch_block = [&](std::int64_t b) {
-                    const int slot = static_cast<int>(b % kRing);
-                    const unsigned round = static_cast<unsigned>(b / kRing);
-                    if (round > 0) {
-                        // every warp is past the block that used this slot
-                        mbar_wait(bar_empty + 8 * slot, (round - 1) & 1u);
-                    }
-                    const std::int64_t pbj = UPPER ? nb - 1 - b : b;
+                // ---- staging of x blocks: progress vector (L2) -> ring slot.
+                //      Blocks are claimed strictly in order (`next_fetch`).
+                //      * A warp that NEEDS block jj and finds it unclaimed
+                //        claims it and polls until it is there: it would have
+                //        to wait for it anyway.
+                //      * Ahead of need, block b is looked at once -- without
+                //        waiting -- by warp b % 16 when that warp starts a
+                //        panel up to kLookAhead blocks earlier, and staged only
+                //        if it has been published completely.  Never is a warp
+                //        parked on a block of the future while panels whose x
+                //        is already there are waiting for it (that cost a
+                //        caught-up CTA three panels of delay per block).
+                auto load_block = [&](std::int64_t blk, Ar (&v)[4]) {
+                    const std::int64_t pbj = UPPER ? nb - 1 - blk : blk;
                     const std::int64_t base = pbj * kB + 4 * lane;
-                    Ar v[4];
                     bool missing = false;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        v[e] = Ar{0};
-                        if (base + e < n) {
+                        if (base + e < n &&
+                            (Sentinel<Ar>::is(v[e]))) {
                             v[e] = ld_volatile(xs + base + e);
                             missing = missing || Sentinel<Ar>::is(v[e]);
                         }
                     }
-                    while (missing) {
-                        missing = false;
+                    return __any_sync(0xffffffffu, missing);
+                };
+                auto init_block = [&](std::int64_t blk, Ar (&v)[4]) {
+                    const std::int64_t pbj = UPPER ? nb - 1 - blk : blk;
+                    const std::int64_t base = pbj * kB + 4 * lane;
+                    Ar sentinel;
+                    memset(&sentinel, 0xff, sizeof(Ar));
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (base + e < n && Sentinel<Ar>::is(v[e])) {
-                                v[e] = ld_volatile(xs + base + e);
-                                missing = missing || Sentinel<Ar>::is(v[e]);
-                            }
-                        }
+                    for (int e = 0; e < 4; ++e) {
+                        v[e] = (base + e < n) ? sentinel : Ar{0};
+                    }
+                };
+                auto publish_block = [&](std::int64_t blk, const Ar (&v)[4]) {
+                    const int slot = static_cast<int>(blk % kRing);
+                    const unsigned round = static_cast<unsigned>(blk / kRing);
+                    if (round > 0) {
+                        // every warp is past the block that used this slot
+                        mbar_wait(bar_empty + 8 * slot, (round - 1) & 1u);
                     }
                     Ar* dst = ring + slot * kB + 4 * lane;
 #pragma unroll
@@ -656,27 +663,48 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                         mbar_arrive(bar_full + 8 * slot);
                     }
                 };
-                // make sure blocks up to `upto` are staged or being staged:
-                // claim (in order) whatever nobody has claimed yet
-                auto stage_ahead = [&](std::int64_t upto) {
-                    upto = upto < ring_panels - 1 ? upto : ring_panels - 1;
+                auto try_claim = [&](std::int64_t blk) {
+                    unsigned won = 0u;
+                    if (lane == 0) {
+                        won = atomicCAS(&next_fetch, static_cast<unsigned>(blk),
+                                        static_cast<unsigned>(blk) + 1u) ==
+                              static_cast<unsigned>(blk);
+                    }
+                    return __shfl_sync(0xffffffffu, won, 0) != 0u;
+                };
+                auto first_unclaimed = [&]() {
+                    unsigned cur = 0u;
+                    if (lane == 0) {
+                        cur = *reinterpret_cast<volatile unsigned*>(&next_fetch);
+                    }
+                    return static_cast<std::int64_t>(
+                        __shfl_sync(0xffffffffu, cur, 0));
+                };
+                // block jj is needed now
+                auto ensure_staged = [&](std::int64_t jj) {
                     for (;;) {
-                        unsigned b = 0xffffffffu;  // nothing to do
-                        if (lane == 0) {
-                            const unsigned cur =
-                                *reinterpret_cast<volatile unsigned*>(&next_fetch);
-                            if (static_cast<std::int64_t>(cur) <= upto) {
-                                b = (atomicCAS(&next_fetch, cur, cur + 1u) == cur)
-                                        ? cur
-                                        : 0xfffffffeu;  // lost: look again
+                        const std::int64_t cur = first_unclaimed();
+                        if (cur > jj) {
+                            return;  // claimed by somebody: wait on `full`
+                        }
+                        if (try_claim(cur)) {
+                            Ar v[4];
+                            init_block(cur, v);
+                            while (load_block(cur, v)) {
                             }
+                            publish_block(cur, v);
                         }
-                        b = __shfl_sync(0xffffffffu, b, 0);
-                        if (b == 0xffffffffu) {
-                            break;
-                        }
-                        if (b != 0xfffffffeu) {
-                            fetch_block(b);
+                    }
+                };
+                // look once at the next unclaimed block if it is this warp's
+                auto stage_ahead = [&](std::int64_t jj) {
+                    const std::int64_t cur = first_unclaimed();
+                    if (cur > jj && cur <= jj + kLookAhead && cur < ring_panels &&
+                        (cur & 15) == warp) {
+                        Ar v[4];
+                        init_block(cur, v);
+                        if (!load_block(cur, v) && try_claim(cur)) {
+                            publish_block(cur, v);
                         }
                     }
                 };
@@ -707,7 +735,8 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                             }
                         }
                         if (jj < ring_panels) {
-                            stage_ahead(jj + kLookAhead);
+                            ensure_staged(jj);
+                            stage_ahead(jj);
                             mbar_wait(bar_full + 8 * slot,
                                       static_cast<unsigned>(jj / kRing) & 1u);
                             if (group_blocks > 0 && jj % group_blocks == 0) {
@@ -768,47 +797,45 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
 
                 // ---- the tile of the block solved LAST is read in the quad
                 //      layout, sub-block by sub-block as the pushes arrive.  A
-                //      thread's share of a 32-column sub-block is two quads; a
-                //      window of TWO sub-blocks is kept in registers (the whole
-                //      tile would be 32 / 64 registers for fp32 / fp64
-                //      storage), the slot a consumed sub-block frees is
-                //      refilled with the one that arrives two chain links
-                //      later.  The first two are requested while the last
-                //      streamed chunk is still being waited for: nothing of
-                //      this tile's latency may end up behind the arrival of x.
+                //      thread's share of a 32-column sub-block is two quads.  The
+                //      first two sub-blocks are requested while the last
+                //      streamed chunk is still being waited for (its "next
+                //      chunk" buffer is free by then), the other two as soon as
+                //      the streaming buffers are dead: nothing of this tile's
+                //      latency may end up behind the arrival of x.  (A rolling
+                //      window of two sub-blocks, refilled after each arrival,
+                //      exposed an L2 round trip per pair whenever the CTA was
+                //      not early.)
                 const bool has_tail = real && deps > 0;
-                Quad<St> wq[2][2];
+                Quad<St> wq[kNSB][2];
                 // t-th sub-block (in arrival order) of the last block's tile
+                // (lower triangle: the last block's tile never reaches past the
+                // end of the matrix; upper triangle: only for the second block
+                // row of the solve order when n is not a multiple of 128)
+                const std::int64_t pb_last = UPPER ? pb + 1 : pb - 1;
+                const bool tail_edge = has_tail && (pb_last + 1) * kB > n;
                 auto load_sub = [&](int t, Quad<St> (&dst)[2]) {
                     const int sbm = UPPER ? kNSB - 1 - t : t;
-                    const std::int64_t pbl = UPPER ? pb + 1 : pb - 1;
                     std::int64_t r = r0 + trow;
                     r = (r < n) ? r : n - 1;
-                    const std::int64_t col = pbl * kB + 32 * sbm + kEPL * seg;
-                    const St* src = A + r * lda + col;
-                    if (col + 16 + kEPL <= n) {
-                        dst[0] = load_quad<St, VW>(src, kEPL);
-                        dst[1] = load_quad<St, VW>(src + 16, kEPL);
-                    } else {
-#pragma unroll
-                        for (int ii = 0; ii < 2; ++ii) {
-                            const std::int64_t left = n - (col + 16 * ii);
-                            const int valid =
-                                left >= kEPL
-                                    ? kEPL
-                                    : (left > 0 ? static_cast<int>(left) : 0);
-                            dst[ii] = load_quad_edge<St>(src + 16 * ii, valid);
-                        }
-                    }
+                    const St* src =
+                        A + r * lda + pb_last * kB + 32 * sbm + kEPL * seg;
+                    dst[0] = load_quad<St, VW>(src, kEPL);
+                    dst[1] = load_quad<St, VW>(src + 16, kEPL);
                 };
                 auto load_tail_window = [&]() {
-                    if (has_tail) {
+                    if (has_tail && !tail_edge) {
                         load_sub(0, wq[0]);
                         load_sub(1, wq[1]);
                     }
                 };
 
-                // ---- streamed panels: register double buffer
+                // ---- streamed panels: register double buffer.  The last one or
+                //      two chunks are peeled off the loop so that the tail
+                //      window can be requested right before the LAST chunk is
+                //      waited for without being live inside the loop (inside it
+                //      the window's registers turned into spill traffic as
+                //      large as the matrix stream itself for fp64 storage).
                 {
                     Span<St> buf_a[RW];
                     Span<St> buf_b[RW];
@@ -817,29 +844,34 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                         if (group_blocks > 0) {
                             l2_prefetch_group(0);
                         }
+                    }
+                    std::int64_t it = 0;
+#pragma unroll 1
+                    for (; it + 2 < items; it += 2) {
+                        load_chunk(it + 1, buf_b);
+                        consume(it, buf_a);
+                        load_chunk(it + 2, buf_a);
+                        consume(it + 1, buf_b);
+                    }
+                    // chunk `it` (if any) is in buf_a
+                    if (items - it == 2) {
+                        load_chunk(it + 1, buf_b);
+                        consume(it, buf_a);
+                        load_tail_window();
+                        consume(it + 1, buf_b);
+                    } else if (items - it == 1) {
+                        load_tail_window();
+                        consume(it, buf_a);
                     } else {
                         load_tail_window();
-                    }
-#pragma unroll 1
-                    for (std::int64_t it = 0; it < items; it += 2) {
-                        if (it + 1 < items) {
-                            load_chunk(it + 1, buf_b);
-                        } else {
-                            load_tail_window();
-                        }
-                        consume(it, buf_a);
-                        if (it + 1 < items) {
-                            if (it + 2 < items) {
-                                load_chunk(it + 2, buf_a);
-                            } else {
-                                load_tail_window();
-                            }
-                            consume(it + 1, buf_b);
-                        }
                     }
                 }
                 if (real) {
                     ACCBLAS_TRACE(3, clock64());
+                }
+                if (has_tail && !tail_edge) {
+                    load_sub(2, wq[2]);
+                    load_sub(3, wq[3]);
                 }
                 {
                     Ar v[RW];
@@ -856,81 +888,93 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_cluster_kernel(
                         rhs_cur[trow] -= streamed;
                     }
                 }
-                if (has_tail) {
+                if (tail_edge) {
+                    // the rare tile that straddles the end of the matrix:
+                    // whole block at once, element by element
+                    if (crank == 0 && warp == 0) {
+                        const std::int64_t room = n - pb_last * kB;
+                        deliver_from_l2<Ar, UPPER>(
+                            xs + pb_last * kB,
+                            room < kB ? static_cast<int>(room) : kB, 0, kNSB - 1,
+                            self_push, self_bar, lane);
+                    }
+#pragma unroll 1
+                    for (int t = 0; t < kNSB; ++t) {
+                        mbar_wait_cluster(bar_push + 8 * t, 0u);
+                    }
+                    std::int64_t r = r0 + trow;
+                    r = (r < n) ? r : n - 1;
+                    const St* src = A + r * lda + pb_last * kB;
+                    const int cols = static_cast<int>(n - pb_last * kB);
+                    Ar v = Ar{};
+#pragma unroll 1
+                    for (int c = seg; c < cols; c += 4) {
+                        v = fma_ar(to_ar<Ar, St>(src[c]), xpush[c], v);
+                    }
+                    v += shfl_xor(v, 1);
+                    v += shfl_xor(v, 2);
+                    if (seg == 0 && r0 + trow < n) {
+                        rhs_cur[trow] -= v;
+                    }
+                } else if (has_tail) {
                     Ar a0 = Ar{}, a1 = Ar{};
                     int l2_next = 0;  // arrivals delivered by warp 0
-                    // (a run-time loop over PAIRS of arrivals, slot = parity:
-                    // fully unrolled, ptxas hoisted the address arithmetic of
-                    // all arrivals and spilled)
-#pragma unroll 1
-                    for (int g2 = 0; g2 < kNSB; g2 += 2) {
 #pragma unroll
-                        for (int slot = 0; slot < 2; ++slot) {
-                            const int t = g2 + slot;
-                            const int sbm = UPPER ? kNSB - 1 - t : t;
-                            // a predecessor outside this cluster publishes
-                            // through L2 only: warp 0 polls the progress vector
-                            // and delivers with the st.async a neighbour would
-                            // have used
-                            if (crank == 0 && warp == 0) {
-                                const std::int64_t pbl = UPPER ? pb + 1 : pb - 1;
-                                const std::int64_t room = n - pbl * kB;
-                                l2_next = deliver_from_l2<Ar, UPPER>(
-                                    xs + pbl * kB,
-                                    room < kB ? static_cast<int>(room) : kB,
-                                    l2_next, t, self_push, self_bar, lane);
-                            }
-                            // The very last sub-block is widened BEFORE the
-                            // wait (its conversions would sit on the critical
-                            // path); the others are widened after their own
-                            // wait, in the shadow of the next one.
-                            const bool ahead = t == kNSB - 1;
-                            Ar cv[2][kEPL];
-                            if (ahead) {
-#pragma unroll
-                                for (int ii = 0; ii < 2; ++ii) {
-                                    wq[slot][ii].pin();
-#pragma unroll
-                                    for (int e = 0; e < kEPL; ++e) {
-                                        cv[ii][e] =
-                                            wq[slot][ii].template get<Ar>(e);
-                                        pin_register(cv[ii][e]);
-                                    }
-                                }
-                            }
-                            mbar_wait_cluster(bar_push + 8 * t, 0u);
-                            if (TRACE && trace != nullptr && tid == 0) {
-                                trace[k * 64 + 44 + t] =
-                                    static_cast<long long>(globaltimer_ns());
-                            }
-                            const Ar* xb = xpush + kEPL * seg;
-                            if (!ahead) {
-#pragma unroll
-                                for (int ii = 0; ii < 2; ++ii) {
-                                    wq[slot][ii].pin();
-#pragma unroll
-                                    for (int e = 0; e < kEPL; ++e) {
-                                        cv[ii][e] =
-                                            wq[slot][ii].template get<Ar>(e);
-                                    }
-                                }
-                            }
-                            if (t + 2 < kNSB) {
-                                // the slot is free: the sub-block that arrives
-                                // two links later takes it
-                                load_sub(t + 2, wq[slot]);
-                            }
+                    for (int t = 0; t < kNSB; ++t) {
+                        const int sbm = UPPER ? kNSB - 1 - t : t;
+                        // a predecessor outside this cluster publishes through
+                        // L2 only: warp 0 polls the progress vector and
+                        // delivers with the st.async a neighbour would have used
+                        if (crank == 0 && warp == 0) {
+                            const std::int64_t room = n - pb_last * kB;
+                            l2_next = deliver_from_l2<Ar, UPPER>(
+                                xs + pb_last * kB,
+                                room < kB ? static_cast<int>(room) : kB, l2_next,
+                                t, self_push, self_bar, lane);
+                        }
+                        // The very last sub-block is widened BEFORE the wait
+                        // (its conversions would sit on the critical path); the
+                        // others are widened after their own wait, in the
+                        // shadow of the next one.
+                        const bool ahead = t == kNSB - 1;
+                        Ar cv[2][kEPL];
+                        if (ahead) {
 #pragma unroll
                             for (int ii = 0; ii < 2; ++ii) {
-                                const int i = 2 * sbm + ii;
+                                wq[t][ii].pin();
 #pragma unroll
-                                for (int e = 0; e < kEPL; e += 2) {
-                                    const Pair<Ar> p2 =
-                                        *reinterpret_cast<const Pair<Ar>*>(
-                                            xb + 16 * i + e);
-                                    a0 = fma_ar(cv[ii][e], p2.a, a0);
-                                    a1 = fma_ar(cv[ii][e + 1], p2.b, a1);
+                                for (int e = 0; e < kEPL; ++e) {
+                                    cv[ii][e] = wq[t][ii].template get<Ar>(e);
+                                    pin_register(cv[ii][e]);
                                 }
+                            }
+                        }
+                        mbar_wait_cluster(bar_push + 8 * t, 0u);
+                        if (TRACE && trace != nullptr && tid == 0) {
+                            trace[k * 64 + 44 + t] =
+                                static_cast<long long>(globaltimer_ns());
+                        }
+                        const Ar* xb = xpush + kEPL * seg;
+                        if (!ahead) {
+#pragma unroll
+                            for (int ii = 0; ii < 2; ++ii) {
+                                wq[t][ii].pin();
+#pragma unroll
+                                for (int e = 0; e < kEPL; ++e) {
+                                    cv[ii][e] = wq[t][ii].template get<Ar>(e);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int ii = 0; ii < 2; ++ii) {
+                            const int i = 2 * sbm + ii;
+#pragma unroll
+                            for (int e = 0; e < kEPL; e += 2) {
+                                const Pair<Ar> p2 =
+                                    *reinterpret_cast<const Pair<Ar>*>(
+                                        xb + 16 * i + e);
+                                a0 = fma_ar(cv[ii][e], p2.a, a0);
+                                a1 = fma_ar(cv[ii][e + 1], p2.b, a1);
                             }
                         }
                     }

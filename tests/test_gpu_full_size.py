@@ -194,7 +194,7 @@ def test_dot_beyond_int32(handle):
         assert abs(float(res[0]) - want) <= tol * scale, (float(res[0]), want)
     # the same through the scalar (strided) kernel on a 2^31+ index range
     res = torch.zeros(1, dtype=torch.float64, device=DEV)
-    handle.dot(torch.float64, n // 2, x, 2, y, 2, res)
+    handle.dot(torch.float64, (n + 1) // 2, x, 2, y, 2, res)     # indices 0, 2, ..., n - 1
     want2 = 0.0
     for i in range(0, n, step):
         want2 += float(torch.dot(x[i:i + step:2].double(), y[i:i + step:2].double()))

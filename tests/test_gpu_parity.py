@@ -508,7 +508,7 @@ def test_trsv_wait_modes_give_identical_results(oracle, ab, handle, variant, who
                 exact = oracle.exact_trsv(A, n, lda, b, upper, unit)
                 assert oracle.l1_rel_error(exact, outs[0]) <= TRSV_TOL[(ar, st)] * n / 300
     finally:
-        ab.tune("trsv_variant", 0)
+        ab.tune("trsv_variant", -1)
         ab.tune("trsv_whole_block_spin", 1)
         ab.tune("trsv_l2_ahead", 1024)
 
@@ -536,7 +536,7 @@ def test_trsv_both_kernels_meet_the_reference_bar(oracle, ab, handle, ar, st, n)
                 err = oracle.l1_rel_error(exact, host(xd))
                 assert err <= 3.0 * ref_err + 1e-15, (variant, upper, unit, err, ref_err)
     finally:
-        ab.tune("trsv_variant", 0)
+        ab.tune("trsv_variant", -1)
 
 
 def test_strided_gemv_then_trsv_share_the_workspace(oracle, ab, handle):

@@ -135,7 +135,8 @@ del g
 b64 = torch.empty(nt, dtype=f64, device=dev)
 h.fill_uniform(nt, 1, b64, 1, 42, nt * nt)
 for tri, upper, unit, mat in (("lower/unit (L)", False, True, LU.contiguous().view(-1)),
-                              ("upper/unit (L^T)", True, True, LU.t().contiguous().view(-1))):
+                              ("upper/unit (L^T)", True, True, LU.t().contiguous().view(-1)),
+                              ("lower/non-unit (U^T)", False, False, LU.t().contiguous().view(-1))):
     xref = b64.clone()
     ref.trsv(f64, upper, unit, nt, mat, nt, xref, 1, plain=True)
     ref.sync()
@@ -172,10 +173,11 @@ for tri, upper, unit, mat in (("lower/unit (L)", False, True, LU.contiguous().vi
 
 out = ROOT / "gpurun_out"
 out.mkdir(exist_ok=True)
-(out / "compare_reference.json").write_text(json.dumps(rows, indent=1))
+tag = sys.argv[1] if len(sys.argv) > 1 else "compare_reference"
+(out / f"{tag}.json").write_text(json.dumps(rows, indent=1))
 lines = ["| op | size | implementation | pair | ms (min of 10) | GB/s | rel. error |",
          "|---|---|---|---|---|---|---|"]
 for r in rows:
     lines.append(f"| {r['op']} | {r['size']} | {r['impl']} | {r['pair']} | {r['ms']:.4f} | "
                  f"{r['GBps']:.0f} | {r['rel_error']:.3e} |")
-(out / "compare_reference.md").write_text("\n".join(lines) + "\n")
+(out / f"{tag}.md").write_text("\n".join(lines) + "\n")

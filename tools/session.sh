@@ -13,10 +13,22 @@ for step in "$@"; do
     pytest) timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${tag}_pytest.log ;;
     pytestall) timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/${tag}_pytest.log ;;
     sweep)  timeout 600 python tools/sweep_dot_fill.py > gpurun_out/${tag}_sweep.log 2>&1; echo "sweep rc=$?" ;;
+    sweep2) timeout 600 python tools/sweep_dot2.py > gpurun_out/${tag}_sweep2.log 2>&1; echo "sweep2 rc=$?" ;;
+    multi)  timeout 900 python -m pytest tests/test_gpu_multi.py -q -x > gpurun_out/${tag}_multi.log 2>&1; echo "multi rc=$?"; tail -5 gpurun_out/${tag}_multi.log ;;
+    multibench) for n in "$@"; do :; done
+            for n in 1 2 4 8; do
+              if [ $n -le $(nvidia-smi -L | wc -l) ]; then
+                if [ $n -eq 1 ]; then timeout 900 python bench.py --gpus 1 --steps 50 --warmup 5 --no-detail > gpurun_out/${tag}_bench_n$n.json 2> gpurun_out/${tag}_bench_n$n.err
+                else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29700 + n)) bench.py --gpus $n --steps 50 --warmup 5 --no-detail > gpurun_out/${tag}_bench_n$n.json 2> gpurun_out/${tag}_bench_n$n.err; fi
+                echo "bench n=$n rc=$?"; fi
+            done ;;
     bench)  timeout 900 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?" ;;
     benchref) timeout 600 python bench.py --impl reference --steps 10 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "benchref rc=$?" ;;
     smoke)  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" ;;
     compare) timeout 900 python tools/compare_reference.py > gpurun_out/${tag}_compare.log 2>&1; echo "compare rc=$?" ;;
+    ncutrsv) ACCBLAS_PROFILE_TRSV=f64:f32,f64:f64 timeout 300 python tools/profile_target.py trsv > gpurun_out/${tag}_ncu_plain.log 2>&1 && \
+             ACCBLAS_PROFILE_TRSV=f64:f32,f64:f64 timeout 600 ncu --set full --clock-control none --import-source on -k regex:trsv_cluster_kernel -s 1 -c 1 -o gpurun_out/${tag}_trsv_f32 python tools/profile_target.py trsv > gpurun_out/${tag}_ncu.log 2>&1; echo "ncutrsv rc=$?"
+             ACCBLAS_PROFILE_TRSV=f64:f64 timeout 600 ncu --set full --clock-control none --import-source on -k regex:trsv_cluster_kernel -s 1 -c 1 -o gpurun_out/${tag}_trsv_f64 python tools/profile_target.py trsv >> gpurun_out/${tag}_ncu.log 2>&1; echo "ncutrsv2 rc=$?" ;;
     *) echo "unknown step $step" ;;
   esac
 done

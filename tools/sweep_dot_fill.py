@@ -58,7 +58,7 @@ for st in (torch.float64, torch.float32, torch.float16):
         row = []
         for rep in range(2):
             for block in (256, 512, 1024):
-                for unroll in (2, 4):
+                for unroll in (1, 2, 4):
                     mixes = (0, 1) if (st == torch.float32 and ar == torch.float64) else (0,)
                     for mix in mixes:
                         ab.tune("dot_block", block)

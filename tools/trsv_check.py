@@ -110,4 +110,4 @@ for n in ([4096, 16384] if quick else [1024, 4096, 16384, 32768]):
                       f"{'unit' if diag == ab.UNIT else 'nonunit'}: cluster {res[0]:7.1f}  single {res[1]:7.1f}  "
                       f"({res[1] / res[0]:.2f}x)", flush=True)
         del T
-ab.tune("trsv_variant", 0)
+ab.tune("trsv_variant", -1)
