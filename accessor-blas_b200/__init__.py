@@ -154,6 +154,7 @@ class Handle:
 
     def peer_disconnect(self) -> None:
         capi.check(self._lib.accblas_peer_disconnect(self._h))
+        self._peer_group = None
 
     def peer_set_timeout(self, seconds: float) -> None:
         capi.check(self._lib.accblas_peer_set_timeout(self._h, float(seconds)))

@@ -847,11 +847,9 @@ int accblas_tune(const char* key, int value)
     static const Knob knobs[] = {
         {"dot_unroll", &Tuning::dot_unroll, 0, 4},
         {"dot_block", &Tuning::dot_block, 0, 1024},
-        {"dot_ctas_per_sm", &Tuning::dot_ctas_per_sm, 0, 64},
+        {"dot_ctas_per_sm", &Tuning::dot_ctas_per_sm, 0, 32},
         {"dot_pdl", &Tuning::dot_pdl, 0, 1},
         {"dot_intmix", &Tuning::dot_intmix, 0, 1},
-        {"dot_l1", &Tuning::dot_l1, 0, 1},
-        {"dot_waves", &Tuning::dot_waves, 0, 1},
         {"gemv_unroll", &Tuning::gemv_unroll, 0, 4},
         {"gemv_variant", &Tuning::gemv_variant, 0, 5},
         {"gemv_ctas_per_sm", &Tuning::gemv_ctas_per_sm, 0, 32},

@@ -218,8 +218,7 @@ __device__ __forceinline__ void finish_dot(Ar local, Ar* partials,
 // Contiguous operands.  x is 16-byte aligned (after peeling `head` elements);
 // y is aligned to CBY bytes (16 = the same alignment as x).
 // MIX (fp32 storage, fp64 arithmetic only): x widened on the integer pipes.
-template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX,
-          bool L1ALLOC = false>
+template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX>
 __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     const St* __restrict__ x, const St* __restrict__ y, std::int64_t n,
     Ar* __restrict__ partials, unsigned* __restrict__ counter,
@@ -275,15 +274,12 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
         uint4 yr[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            xr[u] = L1ALLOC ? ldg_cached_128_ordered(
-                                  x + base + std::int64_t{u} * BLOCK * VEC)
-                            : ldg_stream_128(
-                                  x + base + std::int64_t{u} * BLOCK * VEC);
+            xr[u] = ldg_stream_128(x + base + std::int64_t{u} * BLOCK * VEC);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            yr[u] = ldg_pieces<CBY, !L1ALLOC>(y + base +
-                                              std::int64_t{u} * BLOCK * VEC);
+            yr[u] = ldg_pieces<CBY, true>(y + base +
+                                          std::int64_t{u} * BLOCK * VEC);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
@@ -420,15 +416,14 @@ __global__ __launch_bounds__(BLOCK) void dot_strided_kernel(
                           counter, result, res_dtype, scratch, px);
 }
 
-template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX,
-          bool L1ALLOC = false>
+template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX>
 int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
                   void* result, int res, int ctas_per_sm, cudaStream_t stream,
                   const PeerExchange& px, int head)
 {
     constexpr int VEC = vec_traits<St>::elems;
     constexpr std::int64_t TILE = std::int64_t{BLOCK} * VEC * UNROLL;
-    auto kernel = dot_stream_kernel<St, Ar, BLOCK, UNROLL, CBY, MIX, L1ALLOC>;
+    auto kernel = dot_stream_kernel<St, Ar, BLOCK, UNROLL, CBY, MIX>;
     // one resident wave: every CTA of the grid-stride loop is on the machine
     // from start to end (a partial second wave would leave a tail).  The
     // occupancy is a property of (instantiation, device).
@@ -444,9 +439,9 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
             resident_on[slot] = resident;
         }
     }
-    // (experiment `dot_waves`: more CTAs than are resident, i.e. several
-    // waves of shorter CTAs, the reference's launch shape)
-    if (ctas_per_sm <= 0 || (ctas_per_sm > resident && tuning().dot_waves == 0)) {
+    // (several waves of shorter CTAs -- the reference's launch shape -- and
+    // loads that allocate in L1 were measured too: no gain, profiles/r02_sweep.txt)
+    if (ctas_per_sm <= 0 || ctas_per_sm > resident) {
         ctas_per_sm = resident;
     }
     std::int64_t tiles = n / TILE;
@@ -500,18 +495,6 @@ int launch_shape(Handle* h, std::int64_t n, const void* x, const void* y,
         block = (sizeof(St) == 8 && sizeof(Ar) == 8) ? 1024 : 256;
     }
     const int cps = t.dot_ctas_per_sm;
-    if constexpr (CBY == 16 && !MIX) {
-        // experiment `dot_l1`: the stream allocates in L1 (plain read-only
-        // loads, as the reference's scalar kernel issues them)
-        if (t.dot_l1 != 0 && unroll == 4) {
-            if (block == 1024) {
-                return launch_stream<St, Ar, 1024, 4, 16, false, true>(
-                    h, n, x, y, result, res, cps, stream, px, head);
-            }
-            return launch_stream<St, Ar, 256, 4, 16, false, true>(
-                h, n, x, y, result, res, cps, stream, px, head);
-        }
-    }
 #define ACCBLAS_DOT_SHAPE(B, U)                                               \
     if (block == B && unroll == U) {                                          \
         return launch_stream<St, Ar, B, U, CBY, MIX>(h, n, x, y, result, res, \

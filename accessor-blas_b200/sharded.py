@@ -106,10 +106,20 @@ def connect_peers(handle, group=None) -> bool:
     rank = dist.get_rank(group)
     if world < 2 or world > 8:
         return False
+    key = (id(group), world, rank)
+    if getattr(handle, "_peer_group", None) == key:
+        return True          # this handle already belongs to this group
+    if getattr(handle, "_peer_group", None) is not None:
+        # a handle belongs to one group at a time: leave the old one first (every
+        # rank does, after the group's last call has completed everywhere)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        handle.peer_disconnect()
     mine = handle.peer_export()
     gathered = [None] * world
     dist.all_gather_object(gathered, mine, group=group)
     handle.peer_connect_ipc(world, rank, b"".join(gathered))
+    handle._peer_group = key
     # no barrier needed: the mailbox was zeroed when it was exported and connect
     # does not touch it, so an entry a faster peer publishes right away stays
     return True

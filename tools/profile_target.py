@@ -10,7 +10,7 @@ sys.path.insert(0, str(ROOT))
 import accessor_blas_b200 as ab  # noqa: E402
 
 # usage: profile_target.py [gemv] [dot] [trsv] [key=value ...]   (key=value -> accblas_tune)
-which = {a for a in sys.argv[1:] if "=" not in a} or {"gemv", "dot", "trsv"}
+which = {a for a in sys.argv[1:] if "=" not in a} or {"gemv", "dot", "trsv", "fixtures"}
 for a in sys.argv[1:]:
     if "=" in a:
         key, value = a.split("=")
@@ -66,4 +66,17 @@ if "trsv" in which:
             h.trsv(DT[ar_s], ab.LOWER, ab.UNIT, n, A, n, x, 1)
         torch.cuda.synchronize()
     del LU
+if "fixtures" in which:
+    cnt = 2 ** 28
+    src = torch.empty(cnt, dtype=f64, device=dev)
+    for _ in range(2):
+        h.fill_uniform(1, cnt, src, cnt, 42, 0)
+    for st in (f32, f16):
+        out = torch.empty(cnt, dtype=st, device=dev)
+        for _ in range(2):
+            h.fill_uniform(1, cnt, out, cnt, 42, 0)
+            h.convert(1, cnt, src, cnt, out, cnt)
+        torch.cuda.synchronize()
+        del out
+    del src
 print("profile target done")

@@ -13,7 +13,6 @@ for step in "$@"; do
     pytest) timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${tag}_pytest.log ;;
     pytestall) timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/${tag}_pytest.log ;;
     sweep)  timeout 600 python tools/sweep_dot_fill.py > gpurun_out/${tag}_sweep.log 2>&1; echo "sweep rc=$?" ;;
-    sweep2) timeout 600 python tools/sweep_dot2.py > gpurun_out/${tag}_sweep2.log 2>&1; echo "sweep2 rc=$?" ;;
     multi)  timeout 900 python -m pytest tests/test_gpu_multi.py -q -x > gpurun_out/${tag}_multi.log 2>&1; echo "multi rc=$?"; tail -5 gpurun_out/${tag}_multi.log ;;
     multibench) for n in "$@"; do :; done
             for n in 1 2 4 8; do
@@ -29,6 +28,12 @@ for step in "$@"; do
     ncutrsv) ACCBLAS_PROFILE_TRSV=f64:f32,f64:f64 timeout 300 python tools/profile_target.py trsv > gpurun_out/${tag}_ncu_plain.log 2>&1 && \
              ACCBLAS_PROFILE_TRSV=f64:f32,f64:f64 timeout 600 ncu --set full --clock-control none --import-source on -k regex:trsv_cluster_kernel -s 1 -c 1 -o gpurun_out/${tag}_trsv_f32 python tools/profile_target.py trsv > gpurun_out/${tag}_ncu.log 2>&1; echo "ncutrsv rc=$?"
              ACCBLAS_PROFILE_TRSV=f64:f64 timeout 600 ncu --set full --clock-control none --import-source on -k regex:trsv_cluster_kernel -s 1 -c 1 -o gpurun_out/${tag}_trsv_f64 python tools/profile_target.py trsv >> gpurun_out/${tag}_ncu.log 2>&1; echo "ncutrsv2 rc=$?" ;;
+    profile) export ACCBLAS_PROFILE_TRSV=f64:f32,f64:f64,f32:f32,f64:f16
+             timeout 600 python tools/profile_target.py > gpurun_out/${tag}_prof_plain.log 2>&1 && \
+             timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"gemv_stream|dot_stream|trsv_kernel|trsv_cluster|fill_linear|convert_kernel" -o gpurun_out/${tag}_prof python tools/profile_target.py > gpurun_out/${tag}_prof_ncu.log 2>&1; echo "profile rc=$?"
+             ncu -i gpurun_out/${tag}_prof.ncu-rep --page raw --csv > gpurun_out/${tag}_prof_raw.csv 2>/dev/null; rm -f gpurun_out/${tag}_prof.ncu-rep ;;
+    launches) timeout 600 python bench.py --steps 3 --warmup 3 --no-detail --no-config5 > gpurun_out/${tag}_launch_plain.log 2>&1 && \
+             timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_bench_launches.csv python bench.py --steps 3 --warmup 3 --no-detail --no-config5 > gpurun_out/${tag}_launch_ncu.log 2>&1; echo "launches rc=$?" ;;
     *) echo "unknown step $step" ;;
   esac
 done
