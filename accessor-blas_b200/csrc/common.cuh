@@ -274,23 +274,44 @@ __device__ __forceinline__ uint4 ldg_pieces(const void* p)
         }
         r = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
-        // 2-byte aligned (fp16 rows with an odd stride): eight 16-bit loads,
-        // all in flight together, instead of the scalar kernel's one per turn
-        unsigned short hw[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        // 2-byte aligned (fp16 rows with an odd stride or an odd base).  The
+        // 16 bytes start either on a 4-byte boundary -- four 32-bit loads --
+        // or two bytes past one: a 16-bit load, three 32-bit loads, a 16-bit
+        // load (every piece naturally aligned and inside the 16 bytes), put
+        // back together with funnel shifts.  The case is the same for all
+        // lanes of a warp (they read one row, 16 bytes apart).  Five loads at
+        // most instead of the eight 16-bit loads this path started with.
+        auto ld32 = [](const char* q) {
+            unsigned v;
+            if constexpr (STREAM) {
+                asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];"
+                             : "=r"(v) : "l"(q));
+            } else {
+                asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(q));
+            }
+            return v;
+        };
+        auto ld16 = [](const char* q) {
+            unsigned short v;
             if constexpr (STREAM) {
                 asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];"
-                             : "=h"(hw[i]) : "l"(c + 2 * i));
+                             : "=h"(v) : "l"(q));
             } else {
-                asm volatile("ld.global.nc.u16 %0, [%1];"
-                             : "=h"(hw[i]) : "l"(c + 2 * i));
+                asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(q));
             }
+            return static_cast<unsigned>(v);
+        };
+        if ((reinterpret_cast<std::uintptr_t>(c) & 2u) == 0) {
+            r = make_uint4(ld32(c), ld32(c + 4), ld32(c + 8), ld32(c + 12));
+        } else {
+            const unsigned h0 = ld16(c);
+            const unsigned m0 = ld32(c + 2);
+            const unsigned m1 = ld32(c + 6);
+            const unsigned m2 = ld32(c + 10);
+            const unsigned h7 = ld16(c + 14);
+            r = make_uint4(h0 | (m0 << 16), __funnelshift_r(m0, m1, 16),
+                           __funnelshift_r(m1, m2, 16), (m2 >> 16) | (h7 << 16));
         }
-        r = make_uint4(hw[0] | (static_cast<unsigned>(hw[1]) << 16),
-                       hw[2] | (static_cast<unsigned>(hw[3]) << 16),
-                       hw[4] | (static_cast<unsigned>(hw[5]) << 16),
-                       hw[6] | (static_cast<unsigned>(hw[7]) << 16));
     }
     return r;
 }

@@ -1338,10 +1338,10 @@ int launch_gemv(Handle* h, std::int64_t m, std::int64_t n, double alpha_d,
                         : launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 2, 4>(
                               h, m, n, alpha, A, lda, x, beta, y, incy, stream);
         }
-        if constexpr (sizeof(St) == 2 && sizeof(Ar) == 8) {
-            // fp16 with an odd stride or base (element aligned only), fp64
-            // arithmetic: 2.2 TB/s against 1.35 of the scalar kernel (for
-            // fp32 arithmetic the scalar kernel's 2.4 TB/s stays ahead)
+        if constexpr (sizeof(St) == 2) {
+            // fp16 with an odd stride or base (element aligned only): the same
+            // pipeline, every 16 bytes fetched as 32-bit words (plus two
+            // half-words when they start two bytes past a 4-byte boundary)
             return launch_stream<St, Ar, 4, 2, 1, 8, 3, 1, 2, 2>(
                 h, m, n, alpha, A, lda, x, beta, y, incy, stream);
         }

@@ -117,6 +117,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """N > 1: run this rank on the cores of the NUMA node its GPU hangs off, so
+    that the pinned staging buffers of the host-buffer path (first touch) and
+    the copy-engine traffic stay on the GPU's own socket -- what an MPI launcher
+    with GPU affinity does.  Round 1 measured N concurrent 1 GiB uploads from
+    wherever torchrun happened to place the ranks.  Best effort: returns the
+    node or None."""
+    try:
+        prop = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def time_launches(fn, steps, warmup, torch, barrier=None):
     """ms per step: `warmup` untimed calls, then exactly `steps` calls between
     two CUDA events on the launching (current) stream, synchronised both sides."""
@@ -493,7 +519,9 @@ def run_accblas_arm(args):
         raise RuntimeError("bench.py needs a CUDA device: the accblas path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = None
     if world > 1:
+        numa_node = bind_to_gpu_numa_node(torch, local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     barrier = (lambda: dist.barrier()) if world > 1 else None
@@ -686,7 +714,8 @@ def run_accblas_arm(args):
                          "kernel": "accblas::gemv_stream_kernel<float,double,ROWS=4,UNROLL=2,RG=1,COLW=8>"},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                    "api": "accblas_gemv_host (pinned host buffers)"},
+                    "api": "accblas_gemv_host (pinned host buffers)",
+                    "host_numa_node_rank0": numa_node},
             "gpu_launches": args.steps * world,
             "clocks": clocks,
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}

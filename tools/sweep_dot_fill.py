@@ -39,6 +39,22 @@ for st in (torch.float32, torch.float16):
 del src
 torch.cuda.empty_cache()
 
+print("== GEMV 16384^2 fp16 storage, row stride 16384 + pad elements (GB/s, min of 10) ==", flush=True)
+from bench import gemv_bytes  # noqa: E402
+mg = ng = 16384
+for pad in (0, 4, 2, 1):
+    lda = ng + pad
+    Ah = torch.empty(mg * lda, dtype=torch.float16, device=dev)
+    xh = torch.empty(ng, dtype=torch.float16, device=dev)
+    yh = torch.zeros(mg, dtype=torch.float16, device=dev)
+    h.fill_uniform(mg, lda, Ah, lda, 42, 0)
+    h.fill_uniform(ng, 1, xh, 1, 42, mg * lda)
+    for ar in (torch.float64, torch.float32):
+        ms = min_of_10(lambda: h.gemv(ar, mg, ng, 1.0, Ah, lda, xh, 1, 0.0, yh, 1), torch)
+        print(f"gemv Acc<{NAME[ar]},fp16> lda = n + {pad}: {gemv_bytes(mg, ng, 2) / ms / 1e6:7.0f}", flush=True)
+    del Ah, xh, yh
+torch.cuda.empty_cache()
+
 print("== DOT n = 2^28: block x unroll per pair (GB/s) ==", flush=True)
 nd = 2 ** 28
 x64 = torch.empty(nd, dtype=torch.float64, device=dev)
