@@ -845,12 +845,11 @@ int accblas_tune(const char* key, int value)
         int lo, hi;
     };
     static const Knob knobs[] = {
-        {"dot_unroll", &Tuning::dot_unroll, 0, 8},
+        {"dot_unroll", &Tuning::dot_unroll, 0, 4},
         {"dot_block", &Tuning::dot_block, 0, 1024},
         {"dot_ctas_per_sm", &Tuning::dot_ctas_per_sm, 0, 32},
         {"dot_pdl", &Tuning::dot_pdl, 0, 1},
         {"dot_intmix", &Tuning::dot_intmix, 0, 1},
-        {"dot_vecbytes", &Tuning::dot_vecbytes, 8, 16},
         {"gemv_unroll", &Tuning::gemv_unroll, 0, 4},
         {"gemv_variant", &Tuning::gemv_variant, 0, 5},
         {"gemv_ctas_per_sm", &Tuning::gemv_ctas_per_sm, 0, 32},

@@ -72,16 +72,6 @@ struct FloatToDoubleScaled {
     }
 };
 
-// one 8-byte L1-bypassing load in the low half of a vector register set
-__device__ __forceinline__ uint4 ldg_stream_64_as_vec(const void* p)
-{
-    uint4 r = make_uint4(0u, 0u, 0u, 0u);
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];"
-                 : "=r"(r.x), "=r"(r.y)
-                 : "l"(p));
-    return r;
-}
-
 template <typename St>
 __device__ __forceinline__ St raw_elem(const uint4& raw, int i);
 template <>
@@ -228,11 +218,7 @@ __device__ __forceinline__ void finish_dot(Ar local, Ar* partials,
 // Contiguous operands.  x is 16-byte aligned (after peeling `head` elements);
 // y is aligned to CBY bytes (16 = the same alignment as x).
 // MIX (fp32 storage, fp64 arithmetic only): x widened on the integer pipes.
-// VB = bytes per load: 16, or 8 (fp64 storage only: one element per lane and
-// load, a warp covers 256 contiguous bytes -- the request shape of the
-// reference's scalar kernel).
-template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX,
-          int VB = 16>
+template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX>
 __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     const St* __restrict__ x, const St* __restrict__ y, std::int64_t n,
     Ar* __restrict__ partials, unsigned* __restrict__ counter,
@@ -242,9 +228,8 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     // x and y point at the element that falls on x's first 16-byte boundary;
     // `head` (< 16 / sizeof(St)) elements in front of it belong to the operands
     // as well (e.g. x[1:] . y[1:])
-    constexpr int VEC = VB / static_cast<int>(sizeof(St));
+    constexpr int VEC = vec_traits<St>::elems;
     constexpr std::int64_t TILE = std::int64_t{BLOCK} * VEC * UNROLL;
-    static_assert(VB == 16 || (VB == 8 && CBY == 16 && !MIX), "8-byte loads: aligned operands only");
     __shared__ Ar scratch[kWarp];
     if (pdl) {
         // programmatic dependent launch (see gemv.cu): the next kernel of the
@@ -289,22 +274,12 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
         uint4 yr[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            if constexpr (VB == 16) {
-                xr[u] = ldg_stream_128(x + base + std::int64_t{u} * BLOCK * VEC);
-            } else {
-                xr[u] = ldg_stream_64_as_vec(x + base +
-                                             std::int64_t{u} * BLOCK * VEC);
-            }
+            xr[u] = ldg_stream_128(x + base + std::int64_t{u} * BLOCK * VEC);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            if constexpr (VB == 16) {
-                yr[u] = ldg_pieces<CBY, true>(y + base +
-                                              std::int64_t{u} * BLOCK * VEC);
-            } else {
-                yr[u] = ldg_stream_64_as_vec(y + base +
-                                             std::int64_t{u} * BLOCK * VEC);
-            }
+            yr[u] = ldg_pieces<CBY, true>(y + base +
+                                          std::int64_t{u} * BLOCK * VEC);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
@@ -441,15 +416,14 @@ __global__ __launch_bounds__(BLOCK) void dot_strided_kernel(
                           counter, result, res_dtype, scratch, px);
 }
 
-template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX,
-          int VB = 16>
+template <typename St, typename Ar, int BLOCK, int UNROLL, int CBY, bool MIX>
 int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
                   void* result, int res, int ctas_per_sm, cudaStream_t stream,
                   const PeerExchange& px, int head)
 {
-    constexpr int VEC = VB / static_cast<int>(sizeof(St));
+    constexpr int VEC = vec_traits<St>::elems;
     constexpr std::int64_t TILE = std::int64_t{BLOCK} * VEC * UNROLL;
-    auto kernel = dot_stream_kernel<St, Ar, BLOCK, UNROLL, CBY, MIX, VB>;
+    auto kernel = dot_stream_kernel<St, Ar, BLOCK, UNROLL, CBY, MIX>;
     // one resident wave: every CTA of the grid-stride loop is on the machine
     // from start to end (a partial second wave would leave a tail).  The
     // occupancy is a property of (instantiation, device).
@@ -521,23 +495,6 @@ int launch_shape(Handle* h, std::int64_t n, const void* x, const void* y,
         block = (sizeof(St) == 8 && sizeof(Ar) == 8) ? 1024 : 256;
     }
     const int cps = t.dot_ctas_per_sm;
-    if constexpr (sizeof(St) == 8 && CBY == 16 && !MIX) {
-        // fp64 storage: 8-byte loads, one element per lane and load
-        if (t.dot_vecbytes == 8) {
-#define ACCBLAS_DOT_SHAPE8(B, U)                                              \
-    if (block == B && unroll == U) {                                          \
-        return launch_stream<St, Ar, B, U, 16, false, 8>(                     \
-            h, n, x, y, result, res, cps, stream, px, head);                  \
-    }
-            ACCBLAS_DOT_SHAPE8(256, 4)
-            ACCBLAS_DOT_SHAPE8(256, 8)
-            ACCBLAS_DOT_SHAPE8(512, 4)
-            ACCBLAS_DOT_SHAPE8(512, 8)
-            ACCBLAS_DOT_SHAPE8(1024, 4)
-            ACCBLAS_DOT_SHAPE8(1024, 8)
-#undef ACCBLAS_DOT_SHAPE8
-        }
-    }
 #define ACCBLAS_DOT_SHAPE(B, U)                                               \
     if (block == B && unroll == U) {                                          \
         return launch_stream<St, Ar, B, U, CBY, MIX>(h, n, x, y, result, res, \

@@ -21,7 +21,6 @@ for step in "$@"; do
                 else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29700 + n)) bench.py --gpus $n --steps 50 --warmup 5 --no-detail > gpurun_out/${tag}_bench_n$n.json 2> gpurun_out/${tag}_bench_n$n.err; fi
                 echo "bench n=$n rc=$?"; fi
             done ;;
-    sweep8) timeout 600 python tools/sweep_dot8.py > gpurun_out/${tag}_sweep8.log 2>&1; echo "sweep8 rc=$?" ;;
     bench)  timeout 900 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?" ;;
     benchref) timeout 600 python bench.py --impl reference --steps 10 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "benchref rc=$?" ;;
     smoke)  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" ;;
