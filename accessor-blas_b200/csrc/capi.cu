@@ -861,7 +861,7 @@ int accblas_tune(const char* key, int value)
         {"gemv_stages", &Tuning::gemv_stages, 0, 4},
         {"trsv_variant", &Tuning::trsv_variant, -1, 1},
         {"trsv_whole_block_spin", &Tuning::trsv_whole_block_spin, 0, 1},
-        {"trsv_l2_ahead", &Tuning::trsv_l2_ahead, 0, 1 << 20},
+        {"trsv_l2_ahead", &Tuning::trsv_l2_ahead, -1, 1 << 20},
         {"fill_generic", &Tuning::fill_generic, 0, 1},
     };
     if (key == nullptr) {

@@ -707,7 +707,9 @@ int launch_one(std::int64_t n, const St* A, std::int64_t lda, St* x,
     }
     const std::int64_t nb = (n + kB - 1) / kB;
     kernel<<<static_cast<unsigned>(nb), kThreads, smem, stream>>>(
-        n, A, lda, x, incx, xs, ticket, trace, tuning().trsv_l2_ahead,
+        n, A, lda, x, incx, xs, ticket, trace,
+        tuning().trsv_l2_ahead >= 0 ? tuning().trsv_l2_ahead
+                                    : trsv_default_l2_ahead<St, Ar>(),
         tuning().trsv_whole_block_spin);
     ACCBLAS_CUDA(cudaGetLastError());
     return ACCBLAS_OK;

@@ -1192,8 +1192,11 @@ int launch_cluster(Handle* h, std::int64_t n, const St* A, std::int64_t lda,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    const int l2_ahead = tuning().trsv_l2_ahead >= 0
+                             ? tuning().trsv_l2_ahead
+                             : trsv_default_l2_ahead<St, Ar>();
     ACCBLAS_CUDA(cudaLaunchKernelEx(&cfg, kernel, n, A, lda, x, incx, xs, ticket,
-                                    trace, tuning().trsv_l2_ahead));
+                                    trace, l2_ahead));
     return ACCBLAS_OK;
 }
 

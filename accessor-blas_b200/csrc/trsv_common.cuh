@@ -26,6 +26,18 @@ constexpr int kEPL = 4;                    // elements per lane per row
 // always BEHIND the chain (x already there), and the kernel sits at the
 // 128-register limit.  Same box: 415.6 -> 328.7 us without it; the other
 // pairs are within 1-3 % either way and keep it.
+// Default of the L2 look-ahead (trsv_l2_ahead = -1), bytes per row.  Measured
+// on B200 at n = 16384 (profiles/r02_trsv_l2_ahead_ab.txt): it pays for fp64
+// arithmetic on fp32 / fp64 storage (the widest panels and the slowest block
+// iterations), and costs 2-5 % for fp16 storage and for fp32 arithmetic,
+// whose block iterations are short enough for the prefetch instructions
+// themselves to show.
+template <typename St, typename Ar>
+constexpr int trsv_default_l2_ahead()
+{
+    return (sizeof(Ar) == 8 && sizeof(St) >= 4) ? 1024 : 0;
+}
+
 template <typename St, typename Ar>
 struct pre_convert : std::true_type {};
 template <>

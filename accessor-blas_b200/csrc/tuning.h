@@ -23,7 +23,7 @@ struct Tuning {
     int gemv_stages = 0;       // 0 = register path, 2..4 = bulk-copy ring depth
     int trsv_variant = -1;     // -1 = per storage type (measured on B200: the cluster kernel wins for fp16 storage, 12-24 %; the single-CTA kernel for fp32 / fp64 storage), 0 = cluster kernel (DSMEM hand-off), 1 = one CTA per block row through L2
     int trsv_whole_block_spin = 1;  // TRSV variant 1: a caught-up CTA waits for a whole x block (1) or 32 entries at a time (0)
-    int trsv_l2_ahead = 1024;  // TRSV: bytes per row of the groups of off-diagonal tiles requested into L2 one group ahead (0 = off)
+    int trsv_l2_ahead = -1;    // TRSV: bytes per row of the groups of off-diagonal tiles requested into L2 one group ahead (0 = off; -1 = per pair, see trsv_default_l2_ahead)
     int fill_generic = 0;      // fill_uniform: 1 = per-row kernel with __ddiv_rn also for contiguous outputs (A/B check)
 };
 

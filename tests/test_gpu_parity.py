@@ -510,7 +510,7 @@ def test_trsv_wait_modes_give_identical_results(oracle, ab, handle, variant, who
     finally:
         ab.tune("trsv_variant", -1)
         ab.tune("trsv_whole_block_spin", 1)
-        ab.tune("trsv_l2_ahead", 1024)
+        ab.tune("trsv_l2_ahead", -1)
 
 
 @pytest.mark.parametrize("ar,st", [(torch.float64, torch.float32), (torch.float32, torch.float32),
@@ -537,6 +537,96 @@ def test_trsv_both_kernels_meet_the_reference_bar(oracle, ab, handle, ar, st, n)
                 assert err <= 3.0 * ref_err + 1e-15, (variant, upper, unit, err, ref_err)
     finally:
         ab.tune("trsv_variant", -1)
+
+
+def _substitute_lower_unit(A, b, st_np):
+    """Row-by-row forward substitution in fp64 with every solved entry rounded
+    through the storage type (what the accessor write/re-read does)."""
+    n = b.shape[0]
+    x = np.zeros(n, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        for r in range(n):
+            x[r] = np.float64(st_np(b[r] - np.dot(A[r, :r].astype(np.float64), x[:r])))
+    return x
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("ar", AR)
+@pytest.mark.parametrize("st", ST)
+def test_trsv_nonfinite_matrix_entries_propagate(ab, handle, ar, st, variant):
+    """Inf / NaN in off-diagonal tiles poison the solution from their row on and
+    nothing in front of their 32-row sub-block."""
+    n = 300
+    rng = np.random.default_rng(17)
+    A = np.tril(rng.uniform(-1.0, 1.0, (n, n)) / 64.0, -1).astype(NP[st])
+    A[200, 10] = np.inf
+    A[290, 150] = np.nan
+    A[260, 3] = -np.inf
+    b = rng.uniform(-1.0, 1.0, n).astype(NP[st])
+    want = _substitute_lower_unit(A, b, NP[st])
+    try:
+        ab.tune("trsv_variant", variant)
+        xd = dev(b)
+        handle.trsv(ar, ab.LOWER, ab.UNIT, n, dev(A.reshape(-1)), n, xd, 1)
+        torch.cuda.synchronize()
+        got = host(xd).astype(np.float64)
+    finally:
+        ab.tune("trsv_variant", -1)
+    # The diagonal tile is solved in product form (x_g = Inv_g rhs_g - ...): a
+    # non-finite rhs entry meets the structural zeros of Inv_g, so the rows of
+    # ITS 32-row sub-block in front of it may come out NaN where substitution
+    # keeps them finite (documented in DESIGN.md).  Everything in front of that
+    # sub-block is exact, everything from the poisoned row on is non-finite.
+    fin = np.isfinite(want)
+    assert fin[:200].all() and not fin[200:].any()
+    assert np.isfinite(got[:192]).all()
+    assert not np.isfinite(got[200:]).any()
+    assert np.abs(got[:192] - want[:192]).sum() <= TRSV_TOL[(ar, st)] * np.abs(want[:192]).sum()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("ar", AR)
+@pytest.mark.parametrize("st", ST)
+def test_trsv_subnormal_entries_times_huge_solution(ab, handle, ar, st, variant):
+    """Off-diagonal tiles made of SUBNORMAL storage values, solution entries
+    near the top of the storage range: every row of the second and third block
+    row is a sum of (subnormal * huge) products, so a conversion that flushed
+    subnormals shows up entry by entry."""
+    if ar == torch.float32 and st == torch.float64:
+        pytest.skip("fp64 subnormals are zero in fp32 arithmetic")
+    n = 300
+    rng = np.random.default_rng(23)
+    info = np.finfo(NP[st])
+    tiny = float(info.smallest_subnormal)
+    mant = 2 ** (info.nmant - 1)
+    huge = {torch.float16: 3.0e4, torch.float32: 1.0e38, torch.float64: 1.0e300}[st]
+    if ar == torch.float32:
+        huge = min(huge, 1.0e38)
+    A = np.zeros((n, n), dtype=np.float64)
+    A[128:, :128] = rng.integers(-mant, mant, (n - 128, 128)) * tiny
+    A = A.astype(NP[st])
+    assert (np.abs(A[128:, :128]) < float(info.tiny)).all()
+    b = np.zeros(n, dtype=np.float64)
+    b[:128] = rng.uniform(0.5, 1.0, 128) * huge * rng.choice([-1.0, 1.0], 128)
+    b = b.astype(NP[st])
+    want = _substitute_lower_unit(A, b, NP[st])
+    try:
+        ab.tune("trsv_variant", variant)
+        xd = dev(b)
+        handle.trsv(ar, ab.LOWER, ab.UNIT, n, dev(A.reshape(-1)), n, xd, 1)
+        torch.cuda.synchronize()
+        got = host(xd).astype(np.float64)
+    finally:
+        ab.tune("trsv_variant", -1)
+    assert np.isfinite(got).all()
+    assert np.array_equal(got[:128], want[:128])
+    tail = want[128:]
+    assert (tail != 0).sum() > 100
+    # bound per row: storage rounding of the result + accumulation of 128 terms
+    rel = max(2.0 ** -(info.nmant - 1), 2.0 ** -44) if ar == torch.float64 else 1e-4
+    terms = np.abs(A[128:, :128].astype(np.float64)) @ np.abs(want[:128])
+    floor = float(info.smallest_subnormal)
+    assert (np.abs(got[128:] - tail) <= rel * terms + floor).all()
 
 
 def test_strided_gemv_then_trsv_share_the_workspace(oracle, ab, handle):

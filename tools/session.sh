@@ -21,6 +21,8 @@ for step in "$@"; do
                 else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29700 + n)) bench.py --gpus $n --steps 50 --warmup 5 --no-detail > gpurun_out/${tag}_bench_n$n.json 2> gpurun_out/${tag}_bench_n$n.err; fi
                 echo "bench n=$n rc=$?"; fi
             done ;;
+    trsvab) timeout 600 python tools/trsv_ab.py > gpurun_out/${tag}_trsv_ab.log 2>&1; echo "trsvab rc=$?"; tail -30 gpurun_out/${tag}_trsv_ab.log ;;
+    pytrsv) timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py -q -x -k trsv > gpurun_out/${tag}_pytrsv.log 2>&1; echo "pytrsv rc=$?"; tail -5 gpurun_out/${tag}_pytrsv.log ;;
     bench)  timeout 900 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?" ;;
     benchref) timeout 600 python bench.py --impl reference --steps 10 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "benchref rc=$?" ;;
     smoke)  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" ;;

@@ -67,7 +67,7 @@ for st in (torch.float32, torch.float64, torch.float16):
     T.view(n, lda).diagonal().fill_(1.0)
     for ar in (torch.float64, torch.float32):
         for uplo, diag in ((ab.LOWER, ab.UNIT), (ab.UPPER, ab.NON_UNIT)):
-            variants = [("old", None, None), ("g0", 1, 0), ("g1024", 1, 1024)]
+            variants = [("old", None, None), ("new", 1, -1), ("g0", 1, 0), ("g1024", 1, 1024)]
             res = {}
             for rep in range(2):
                 for name, whole, ahead in variants:
@@ -78,7 +78,14 @@ for st in (torch.float32, torch.float64, torch.float16):
                     lib_name = "old" if name == "old" else "new"
                     t = timed(libs[lib_name], handles[lib_name], ar, st, uplo, diag, T, x)
                     res[name] = min(res.get(name, 1e9), t)
+            sols = {}
+            for lib_name in ("old", "new"):
+                x = b.clone()
+                timed(libs[lib_name], handles[lib_name], ar, st, uplo, diag, T, x)
+                sols[lib_name] = x
+            same = bool(torch.equal(sols["old"], sols["new"]))
             print(f"trsv Acc<{NAME[ar]},{NAME[st]}> {'lower' if uplo == ab.LOWER else 'upper'}/"
                   f"{'unit' if diag == ab.UNIT else 'nonunit'}: " +
-                  "  ".join(f"{name} {res[name]:6.1f}" for name, _, _ in variants), flush=True)
+                  "  ".join(f"{name} {res[name]:6.1f}" for name, _, _ in variants) +
+                  f"  bit-identical solutions: {same}", flush=True)
     del T
