@@ -77,13 +77,13 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
     long long* const trace = TRACE ? trace_arg : nullptr;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ar* D = reinterpret_cast<Ar*>(smem_raw);  // kB x kLD
-    Ar* xcol = D + kB * kLD;                  // 2 x kB, staged x blocks
-    Ar* rhs = xcol + 2 * kB;                  // kB
+    Ar* xcol = D + kB * kLD;                  // kXRing x kB, staged x blocks
+    Ar* rhs = xcol + kXRing * kB;             // kB
     Ar* xsol = rhs + kB;                      // kB
     Ar* inv_diag = xsol + kB;                 // kB
     Ar* scratch = inv_diag + kB;              // kB, rehearsal right-hand side
     __shared__ unsigned k_shared;
-    __shared__ int mode_s[2];
+    __shared__ int mode_s[kXRing];
 
     const int tid = threadIdx.x;
     const int lane = tid & (kWarp - 1);
@@ -233,13 +233,27 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
         const std::int64_t pbj = UPPER ? nb - 1 - jj : jj;
         const int pm = UPPER ? NP - 1 - p : p;  // memory panel
         const std::int64_t c0 = pbj * kB + pm * (16 * Q);
+        // Only the LAST physical block can be cut off by the edge of the
+        // matrix, and only `upper` ever streams it (lower: pbj < pb).  Every
+        // other tile takes the path without per-quad edge arithmetic (the
+        // 64-bit compares, selects and reconvergence points of the general
+        // path were ~100 of the ~345 instructions of a warp's block
+        // iteration; ncu source view, session r02z).
+        if (!UPPER || (pbj + 1) * kB <= n) {
 #pragma unroll
-        for (int i = 0; i < Q; ++i) {
-            const std::int64_t col = c0 + 16 * i + kEPL * seg;
-            const std::int64_t left = n - col;
-            const int valid =
-                left >= kEPL ? kEPL : (left > 0 ? static_cast<int>(left) : 0);
-            dst[i] = load_quad<St, VW>(row_ptr + c0 + 16 * i, valid);
+            for (int i = 0; i < Q; ++i) {
+                dst[i] = load_quad<St, VW>(row_ptr + c0 + 16 * i, kEPL);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) {
+                const std::int64_t col = c0 + 16 * i + kEPL * seg;
+                const std::int64_t left = n - col;
+                const int valid =
+                    left >= kEPL ? kEPL
+                                 : (left > 0 ? static_cast<int>(left) : 0);
+                dst[i] = load_quad<St, VW>(row_ptr + c0 + 16 * i, valid);
+            }
         }
     };
     // warp 0: copy the 128 progress-vector entries of physical block `pblock`
@@ -257,6 +271,15 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                          : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // one commit group per block iteration, empty past the last dependency, so
+    // that "all but the kXAhead - 1 youngest groups" is always "block jj"
+    auto prefetch_x_slot = [&](std::int64_t j, std::int64_t deps_, int b) {
+        if (j < deps_) {
+            prefetch_x(UPPER ? nb - 1 - j : j, b);
+        } else {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
     };
     // Ask L2 for the off-diagonal tiles of a GROUP of consecutive blocks of
     // the solve order, one group ahead.  Two reasons:
@@ -283,6 +306,9 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
         c_hi = c_hi < n ? c_hi : n;
         constexpr int kLineElems = 128 / static_cast<int>(sizeof(St));
         const St* row_base = row_ptr - kEPL * seg;
+        // (one cp.async.bulk.prefetch.L2 per row and group instead of one
+        // prefetch per line measured the same: 318 vs 319.5 us, session r02y --
+        // UBLKPF takes uniform registers, so the compiler serialises the lanes)
         for (std::int64_t c = c_lo + seg * kLineElems; c < c_hi;
              c += 4 * kLineElems) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(row_base + c));
@@ -320,7 +346,10 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
         if (deps > 0) {
             load_panel(0, 0, cur);
             if (warp == 0) {
-                prefetch_x(UPPER ? nb - 1 : 0, 0);
+#pragma unroll
+                for (int a = 0; a < kXAhead; ++a) {
+                    prefetch_x_slot(a, deps, a);
+                }
             }
             if (group_blocks > 0) {
                 // the rest of group 0 (block 0 itself is being loaded)
@@ -352,7 +381,8 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                 if (jj == deps - 1) {
                     ACCBLAS_TRACE(3, clock64());
                 }
-                asm volatile("cp.async.wait_all;" ::: "memory");
+                asm volatile("cp.async.wait_group %0;" ::"n"(kXAhead - 1)
+                             : "memory");
                 __syncwarp();  // lanes read entries other lanes copied
 #pragma unroll
                 for (int sb = 0; sb < kNSB; ++sb) {
@@ -487,9 +517,10 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
                         if (first) {
                             fast = mode_s[buf] != 0;
                             // every warp is past block jj - 1: its x buffer
-                            // can take block jj + 1
-                            if (warp == 0 && jj + 1 < deps) {
-                                prefetch_x(UPPER ? nb - 2 - jj : jj + 1, buf ^ 1);
+                            // can take block jj + kXAhead
+                            if (warp == 0) {
+                                prefetch_x_slot(jj + kXAhead, deps,
+                                                (buf + kXAhead) % kXRing);
                             }
                         }
                     }
@@ -525,7 +556,7 @@ __global__ __launch_bounds__(kThreads, 1) void trsv_kernel(
             if (phase_log && fast) {
                 ++ph[4];
             }
-            buf ^= 1;
+            buf = (buf + 1) % kXRing;
         }
         if (real) {
             ACCBLAS_TRACE(5, clock64());
@@ -692,7 +723,7 @@ int launch_one(std::int64_t n, const St* A, std::int64_t lda, St* x,
                cudaStream_t stream)
 {
     auto kernel = trsv_kernel<St, Ar, UPPER, UNIT, VW, TRACE>;
-    const size_t smem = sizeof(Ar) * (kB * kLD + 6 * kB);
+    const size_t smem = sizeof(Ar) * (kB * kLD + (4 + kXRing) * kB);
     // the opt-in is per device (and per instantiation)
     static bool configured[64] = {};
     int device = 0;

@@ -16,6 +16,16 @@ constexpr int kNSB = kB / kSB;
 // 16-byte bank groups (row stride 136 doubles = 68 groups = 4 mod 8).
 constexpr int kLD = kB + 8;
 constexpr int kThreads = 512;
+// x blocks of the single-CTA kernel: fetched kXAhead block iterations ahead of
+// their use into a ring of kXAhead + 1 shared-memory buffers.  One block ahead
+// is enough: three ahead measured the same (319.5 vs 317.5 us Acc<fp64,fp32>,
+// fp32 arithmetic 2 % slower; session r02x) -- the copy's round trip is not
+// what warp 0 waits for at the top of an iteration.
+#ifndef ACCBLAS_TRSV_XAHEAD
+#define ACCBLAS_TRSV_XAHEAD 1
+#endif
+constexpr int kXAhead = ACCBLAS_TRSV_XAHEAD;
+constexpr int kXRing = kXAhead + 1;
 constexpr int kWarps = kThreads / kWarp;
 constexpr int kEPL = 4;                    // elements per lane per row
 // Widen a panel BEFORE its x block is looked at (the conversions are then off

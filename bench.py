@@ -118,29 +118,53 @@ class ClockSampler:
 
 
 def bind_to_gpu_numa_node(torch, local_rank):
-    """N > 1: run this rank on the cores of the NUMA node its GPU hangs off, so
-    that the pinned staging buffers of the host-buffer path (first touch) and
-    the copy-engine traffic stay on the GPU's own socket -- what an MPI launcher
-    with GPU affinity does.  Round 1 measured N concurrent 1 GiB uploads from
-    wherever torchrun happened to place the ranks.  Best effort: returns the
-    node or None."""
+    """N > 1: run this rank on the cores next to its GPU, so that the pinned
+    staging buffers of the host-buffer path (first touch) and the copy-engine
+    traffic stay on the GPU's own socket -- what an MPI launcher with GPU
+    affinity does.  Round 1 measured N concurrent 1 GiB uploads from wherever
+    torchrun happened to place the ranks.  Best effort; returns what was done
+    (and why not) for the bench line."""
+    info = {"bound": False, "source": None, "cpus": None, "node": None, "notes": []}
+    allowed = os.sched_getaffinity(0)
+
+    def apply(cpus, source, node=None):
+        cpus = set(cpus) & allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, source=source, cpus=len(cpus), node=node)
+            return True
+        info["notes"].append(f"{source}: no narrower set than the {len(allowed)} allowed cpus")
+        return False
+
+    bdf = None
     try:
         prop = torch.cuda.get_device_properties(local_rank)
         bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
         node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
         if node < 0:
-            return None
-        cpus = set()
-        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return node
-    except Exception:
-        pass
-    return None
+            info["notes"].append(f"sysfs numa_node of {bdf} is {node}")
+        else:
+            cpus = set()
+            for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            if apply(cpus, "sysfs", node):
+                return info
+    except Exception as exc:  # noqa: BLE001 - diagnostics only
+        info["notes"].append(f"sysfs: {exc!r}")
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = (pynvml.nvmlDeviceGetHandleByPciBusId(bdf.encode()) if bdf
+               else pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        words = (max(allowed) + 64) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(hnd, words)
+        cpus = {64 * w + bit for w, word in enumerate(mask) for bit in range(64) if (int(word) >> bit) & 1}
+        if apply(cpus, "nvml"):
+            return info
+    except Exception as exc:  # noqa: BLE001
+        info["notes"].append(f"nvml: {exc!r}")
+    return info
 
 
 def time_launches(fn, steps, warmup, torch, barrier=None):
@@ -715,7 +739,7 @@ def run_accblas_arm(args):
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                     "api": "accblas_gemv_host (pinned host buffers)",
-                    "host_numa_node_rank0": numa_node},
+                    "host_affinity_rank0": numa_node},
             "gpu_launches": args.steps * world,
             "clocks": clocks,
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}

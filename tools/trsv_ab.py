@@ -67,7 +67,7 @@ for st in (torch.float32, torch.float64, torch.float16):
     T.view(n, lda).diagonal().fill_(1.0)
     for ar in (torch.float64, torch.float32):
         for uplo, diag in ((ab.LOWER, ab.UNIT), (ab.UPPER, ab.NON_UNIT)):
-            variants = [("old", None, None), ("new", 1, -1), ("g0", 1, 0), ("g1024", 1, 1024)]
+            variants = [("old", None, None), ("new", 1, -1), ("sub32", 0, -1), ("g0", 1, 0), ("g1024", 1, 1024)]
             res = {}
             for rep in range(2):
                 for name, whole, ahead in variants:
@@ -75,6 +75,9 @@ for st in (torch.float32, torch.float64, torch.float16):
                     if whole is not None:
                         ab.tune("trsv_whole_block_spin", whole)
                         ab.tune("trsv_l2_ahead", ahead)
+                    if whole is not None:
+                        # sub32 (32 entries at a time) exists in the single-CTA kernel only
+                        ab.tune("trsv_variant", 1 if name == "sub32" else -1)
                     lib_name = "old" if name == "old" else "new"
                     t = timed(libs[lib_name], handles[lib_name], ar, st, uplo, diag, T, x)
                     res[name] = min(res.get(name, 1e9), t)

@@ -29,6 +29,9 @@ st = {"f64": torch.float64, "f32": torch.float32, "f16": torch.float16}[
 ar_code = {"f64": 0, "f32": 1}[sys.argv[3] if len(sys.argv) > 3 else "f64"]
 dev = torch.device("cuda:0")
 h = ab.Handle(0)
+import os
+if "TRSV_VARIANT" in os.environ:   # 1: the single-CTA kernel (its phase sums are printed below)
+    ab.tune("trsv_variant", int(os.environ["TRSV_VARIANT"]))
 lib = capi.load()
 fn = lib.accblas_dev_trsv_trace   # AttributeError: not the development library
 fn.restype = ctypes.c_int
@@ -57,6 +60,12 @@ for it in range(3):
     assert rc == 0, capi.load().accblas_last_error()
     print(f"run {it}: {e0.elapsed_time(e1) * 1e3:.1f} us total")
 t = trace.cpu().numpy().reshape(nb, 64)
+if os.environ.get("TRSV_VARIANT") == "1":
+    ph = t[nb - 1, 48:53]
+    per = ph[:4] / max(nb - 1, 1)
+    print(f"single-CTA kernel, last block row, sums over its {nb - 1} block iterations (cycles; per iteration): "
+          f"x wait+check {ph[0]} ({per[0]:.0f})  loads issued+widen {ph[1]} ({per[1]:.0f})  "
+          f"re-poll+first barrier {ph[2]} ({per[2]:.0f})  FMAs {ph[3]} ({per[3]:.0f})  fast-path iterations {ph[4]}")
 for k in sorted(set([0, 1, 2, 7, 8, 9, nb // 4, nb // 2, nb - 2, nb - 1])):
     if 0 <= k < nb:
         print(f"block {k:4d}: tile {t[k, 1] - t[k, 0]:6d}  invert+products {t[k, 2] - t[k, 1]:6d}  "
