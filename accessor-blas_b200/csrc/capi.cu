@@ -850,6 +850,8 @@ int accblas_tune(const char* key, int value)
         {"dot_ctas_per_sm", &Tuning::dot_ctas_per_sm, 0, 32},
         {"dot_pdl", &Tuning::dot_pdl, 0, 1},
         {"dot_intmix", &Tuning::dot_intmix, 0, 1},
+        {"dot_pool_pct", &Tuning::dot_pool_pct, 0, 100},
+        {"dot_chunk_tiles", &Tuning::dot_chunk_tiles, 1, 4096},
         {"gemv_unroll", &Tuning::gemv_unroll, 0, 4},
         {"gemv_variant", &Tuning::gemv_variant, 0, 5},
         {"gemv_ctas_per_sm", &Tuning::gemv_ctas_per_sm, 0, 32},

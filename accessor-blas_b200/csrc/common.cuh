@@ -84,6 +84,7 @@ constexpr int kCtlDotCounter = 0;    // DOT "blocks done" counter (self-resettin
 constexpr int kCtlTrsvTicket = 1;    // TRSV block-row ticket (self-resetting)
 constexpr int kCtlFillFlag = 2;      // fill_uniform non-normal counter
 constexpr int kCtlErrCounter = 3;    // l1_error "blocks done" counter
+constexpr int kCtlDotChunk = 4;      // DOT: next chunk of the dynamically assigned pool (self-resetting)
 
 inline unsigned* control_words(Handle* h)
 {

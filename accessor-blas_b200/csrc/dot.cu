@@ -184,8 +184,12 @@ template <typename Ar, int BLOCK>
 __device__ __forceinline__ void finish_dot(Ar local, Ar* partials,
                                            unsigned* counter, void* result,
                                            int res_dtype, Ar* scratch,
-                                           const PeerExchange& px)
+                                           const PeerExchange& px,
+                                           unsigned num_partials = 0)
 {
+    // partials[0 .. gridDim.x) = one per CTA; the streaming kernel appends one
+    // per dynamically assigned chunk (num_partials > gridDim.x)
+    num_partials = num_partials ? num_partials : gridDim.x;
     __shared__ bool is_last;
     const Ar total = block_sum(local, scratch);
     if (threadIdx.x == 0) {
@@ -202,7 +206,7 @@ __device__ __forceinline__ void finish_dot(Ar local, Ar* partials,
     }
     __threadfence();
     Ar v = Ar{};
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += BLOCK) {
+    for (unsigned i = threadIdx.x; i < num_partials; i += BLOCK) {
         v += __ldcg(partials + i);
     }
     Ar sum = block_sum(v, scratch);
@@ -212,6 +216,7 @@ __device__ __forceinline__ void finish_dot(Ar local, Ar* partials,
     if (threadIdx.x == 0) {
         store_result(result, res_dtype, sum);
         *counter = 0u;  // re-arm for the next call on this handle
+        counter[kCtlDotChunk - kCtlDotCounter] = 0u;
     }
 }
 
@@ -223,7 +228,7 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     const St* __restrict__ x, const St* __restrict__ y, std::int64_t n,
     Ar* __restrict__ partials, unsigned* __restrict__ counter,
     void* __restrict__ result, int res_dtype, const PeerExchange px, int pdl,
-    int head)
+    int head, std::int64_t static_tiles, int chunk_tiles, unsigned num_chunks)
 {
     // x and y point at the element that falls on x's first 16-byte boundary;
     // `head` (< 16 / sizeof(St)) elements in front of it belong to the operands
@@ -268,7 +273,7 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     }
     float chk = 0.0f;  // MIX: NaN iff an Inf/NaN went through the scaled path
 
-    for (std::int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    auto consume_tile = [&](std::int64_t tile) {
         const std::int64_t base = tile * TILE + std::int64_t{threadIdx.x} * VEC;
         uint4 xr[UNROLL];
         uint4 yr[UNROLL];
@@ -302,6 +307,12 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
                 }
             }
         }
+    };
+    // Static part: tiles [0, static_tiles) in grid-stride order; the rest of
+    // the tiles is handed out dynamically further down.
+    for (std::int64_t tile = blockIdx.x; tile < static_tiles;
+         tile += gridDim.x) {
+        consume_tile(tile);
     }
     if constexpr (MIX) {
         // (block-uniform) an Inf/NaN was consumed by the scaled conversion:
@@ -312,7 +323,7 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
             for (int u = 0; u < UNROLL; ++u) {
                 acc[u][0] = 0.0;
             }
-            for (std::int64_t tile = blockIdx.x; tile < num_tiles;
+            for (std::int64_t tile = blockIdx.x; tile < static_tiles;
                  tile += gridDim.x) {
                 const std::int64_t base =
                     tile * TILE + std::int64_t{threadIdx.x} * VEC;
@@ -351,27 +362,94 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
     }
 
     // fixed-order fold of the per-thread accumulators
-    Ar local = Ar{};
+    auto fold_acc = [&]() {
+        Ar sum = Ar{};
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-        // pairwise fold of the element slots, then the vectors in order
-        Ar v[SLOTS];
+        for (int u = 0; u < UNROLL; ++u) {
+            // pairwise fold of the element slots, then the vectors in order
+            Ar v[SLOTS];
 #pragma unroll
-        for (int i = 0; i < SLOTS; ++i) {
-            v[i] = acc[u][i];
+            for (int i = 0; i < SLOTS; ++i) {
+                v[i] = acc[u][i];
+            }
+#pragma unroll
+            for (int width = SLOTS / 2; width > 0; width /= 2) {
+#pragma unroll
+                for (int i = 0; i < width; ++i) {
+                    v[i] += v[i + width];
+                }
+            }
+            sum += v[0];
         }
+        return sum;
+    };
+    Ar local = fold_acc();
+    local += tail;
+
+    // Dynamic part.  Equal shares are as slow as the slowest SM: on B200 the
+    // SMs do not all get the same share of the memory system (a static
+    // partition measured 6970 GB/s for fp64 storage where the reference's
+    // 32-waves-of-small-blocks kernel, balanced by the block scheduler, reached
+    // 7360 on the same box; profiles/r02_dot_dynamic_ab.txt).  The last ~12 %
+    // of the tiles are therefore handed out in small chunks by an atomic
+    // counter: SMs that finish their static share early take more of them.
+    // Every chunk has its OWN partial sum, folded in chunk order at the end, so
+    // the result does not depend on which CTA happened to take which chunk.
+    if (chunk_tiles > 0) {
+        // One barrier per chunk: the id of the NEXT chunk is fetched while the
+        // current one is streamed (the atomic's round trip stays off the
+        // path), and the warps' sums of a chunk are added up by thread 0 after
+        // the barrier that publishes that id.
+        constexpr int NW = BLOCK / kWarp;
+        __shared__ unsigned chunk_id[2];
+        __shared__ Ar warp_part[2][NW];
+        unsigned* const chunk_counter =
+            counter + (kCtlDotChunk - kCtlDotCounter);
+        const int lane = threadIdx.x & (kWarp - 1);
+        const int warp = threadIdx.x >> 5;
+        if (threadIdx.x == 0) {
+            chunk_id[0] = atomicAdd(chunk_counter, 1u);
+        }
+        __syncthreads();
+        for (int k = 0;; ++k) {
+            const int slot = k & 1;
+            const unsigned c = chunk_id[slot];
+            if (c >= num_chunks) {
+                break;
+            }
+            if (threadIdx.x == 0) {
+                chunk_id[slot ^ 1] = atomicAdd(chunk_counter, 1u);
+            }
 #pragma unroll
-        for (int width = SLOTS / 2; width > 0; width /= 2) {
+            for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-            for (int i = 0; i < width; ++i) {
-                v[i] += v[i + width];
+                for (int i = 0; i < SLOTS; ++i) {
+                    acc[u][i] = Ar{};
+                }
+            }
+            const std::int64_t t0 = static_tiles + std::int64_t{c} * chunk_tiles;
+            const std::int64_t t1 =
+                t0 + chunk_tiles < num_tiles ? t0 + chunk_tiles : num_tiles;
+            for (std::int64_t tile = t0; tile < t1; ++tile) {
+                consume_tile(tile);
+            }
+            const Ar wsum = warp_sum(fold_acc());
+            if (lane == 0) {
+                warp_part[slot][warp] = wsum;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                Ar part = Ar{};
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    part += warp_part[slot][w];
+                }
+                *reinterpret_cast<volatile Ar*>(partials + gridDim.x + c) = part;
             }
         }
-        local += v[0];
     }
-    local += tail;
     finish_dot<Ar, BLOCK>(local, partials, counter, result, res_dtype, scratch,
-                          px);
+                          px, gridDim.x + num_chunks);
 }
 
 // Any stride: scalar loads, four of each operand in flight per thread, 64-bit
@@ -432,8 +510,12 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
     int resident = resident_on[slot];
     if (resident == 0 || slot != h->device) {
         int occ = 0;
+        // (of the conversion-pipe instantiation also for MIX: the integer-
+        // widening variant promises the bits of the same shape, and the grid
+        // is part of the shape)
         ACCBLAS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &occ, kernel, BLOCK, 0));
+            &occ, dot_stream_kernel<St, Ar, BLOCK, UNROLL, CBY, false>, BLOCK,
+            0));
         resident = occ > 0 ? occ : 1;
         if (slot == h->device) {
             resident_on[slot] = resident;
@@ -458,6 +540,29 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
         return rc;
     }
     const int pdl = tuning().dot_pdl;
+    // static share + dynamically assigned pool (see the kernel): the split is
+    // a function of (n, grid) only, so repeated calls add in the same order
+    std::int64_t static_tiles = tiles;
+    int chunk_tiles = 0;
+    std::int64_t num_chunks = 0;
+    const int pool_pct = tuning().dot_pool_pct;
+    if (!MIX && pool_pct > 0 && tiles >= 32 * grid) {
+        std::int64_t pool = tiles * pool_pct / 100;
+        static_tiles = (tiles - pool) / grid * grid;
+        pool = tiles - static_tiles;
+        // the chunk partials share the 64 KiB scratch with the CTA partials
+        const std::int64_t room = max_grid - grid;
+        const std::int64_t max_chunks = room < 4096 ? room : 4096;
+        std::int64_t ct = tuning().dot_chunk_tiles;
+        if (max_chunks > 0 && pool > 0) {
+            const std::int64_t need = (pool + max_chunks - 1) / max_chunks;
+            ct = ct > need ? ct : need;
+            chunk_tiles = static_cast<int>(ct);
+            num_chunks = (pool + ct - 1) / ct;
+        } else {
+            static_tiles = tiles;
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
     cfg.blockDim = dim3(BLOCK);
@@ -470,7 +575,8 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
     ACCBLAS_CUDA(cudaLaunchKernelEx(
         &cfg, kernel, static_cast<const St*>(x), static_cast<const St*>(y), n,
         static_cast<Ar*>(payload(h)), control_words(h) + kCtlDotCounter, result,
-        res, px, pdl, head));
+        res, px, pdl, head, static_tiles, chunk_tiles,
+        static_cast<unsigned>(num_chunks)));
     return ACCBLAS_OK;
 }
 

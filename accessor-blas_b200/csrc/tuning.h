@@ -11,6 +11,8 @@ struct Tuning {
     int dot_block = 0;         // threads per CTA (256 / 512 / 1024); 0 = default (1024 for Acc<fp64,fp64>, else 256)
     int dot_ctas_per_sm = 0;   // grid = SMs * this; 0 = all that are resident
     int dot_pdl = 1;           // programmatic dependent launch for back-to-back DOTs
+    int dot_pool_pct = 12;     // DOT: share of the tiles (%) handed out dynamically in chunks at the end (0 = static partition only)
+    int dot_chunk_tiles = 4;   // DOT: tiles per dynamically assigned chunk (grows with n so that there are at most 4096 chunks)
     int dot_intmix = 0;        // Acc<fp64,fp32>: widen x on the integer pipes (experiment)
     int gemv_unroll = 2;       // vectors per row in flight per lane
     int gemv_variant = 0;      // 0 = auto, 2 = CTA-per-2-rows, 3 = CTA-per-row, 4 = CTA-per-4-rows, 5 = CTA-per-8-rows

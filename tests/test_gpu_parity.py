@@ -398,6 +398,42 @@ def test_dot_result_types_strides_alignment(oracle, handle, st):
 # ---------------------------------------------------------------------------
 # TRSV
 # ---------------------------------------------------------------------------
+@pytest.mark.parametrize("ar", AR)
+@pytest.mark.parametrize("st", ST)
+def test_dot_dynamic_pool_is_deterministic(oracle, ab, handle, ar, st):
+    """The last share of the tiles is handed out by an atomic counter; every
+    chunk has its own partial, folded in chunk order, so which CTA took which
+    chunk must not show in the bits -- and the pool must not lose or double
+    anything (ragged n, more chunks than CTAs)."""
+    n = 2 ** 25 + 12345
+    x = stored(oracle, n, st, seed=42, first=0)
+    y = stored(oracle, n, st, seed=42, first=n)
+    xd, yd = dev(x), dev(y)
+    exact = oracle.exact_dot(x, y, n)
+    res = torch.zeros(1, dtype=ar, device=DEV)
+    try:
+        ab.tune("dot_ctas_per_sm", 1)   # small grid: the pool is active from 32 tiles per CTA on
+        seen = {}
+        for pct, ct in ((12, 4), (12, 4), (12, 4), (50, 1), (50, 1), (0, 4)):
+            ab.tune("dot_pool_pct", pct)
+            ab.tune("dot_chunk_tiles", ct)
+            for _ in range(3):
+                handle.dot(ar, n, xd, 1, yd, 1, res)
+                torch.cuda.synchronize()
+                seen.setdefault((pct, ct), set()).add(res.cpu().numpy().tobytes())
+        for key, bits in seen.items():
+            assert len(bits) == 1, key
+        tol = {torch.float64: 1e-13, torch.float32: 2e-5}[ar]
+        scale = float(np.abs(x.astype(np.float64) * y.astype(np.float64)).sum())
+        for key, bits in seen.items():
+            got = float(np.frombuffer(next(iter(bits)), dtype=NP[ar])[0])
+            assert abs(got - exact) <= tol * scale, (key, got, exact)
+    finally:
+        ab.tune("dot_ctas_per_sm", 0)
+        ab.tune("dot_pool_pct", 12)
+        ab.tune("dot_chunk_tiles", 4)
+
+
 def lu_fixture(n, seed, lda=None):
     """Row-major matrix whose triangles are well conditioned the way the
     reference's fixture is (partially pivoted LU of uniform(-1,1) data,
