@@ -205,11 +205,16 @@ __device__ __forceinline__ void finish_dot(Ar local, Ar* partials,
         return;
     }
     __threadfence();
-    Ar v = Ar{};
+    // The fold of the (up to ~5000) partials runs in fp64 also for fp32
+    // arithmetic and is rounded to Ar once: one CTA, a few values per thread --
+    // free, and the partials of the dynamic pool do not add fp32 rounding
+    // steps to the result.
+    __shared__ double wide_scratch[kWarp];
+    double v = 0.0;
     for (unsigned i = threadIdx.x; i < num_partials; i += BLOCK) {
-        v += __ldcg(partials + i);
+        v += static_cast<double>(__ldcg(partials + i));
     }
-    Ar sum = block_sum(v, scratch);
+    Ar sum = static_cast<Ar>(block_sum(v, wide_scratch));
     if (px.world > 1) {
         sum = peer_allreduce(sum, px);
     }
@@ -427,6 +432,11 @@ __global__ __launch_bounds__(BLOCK) void dot_stream_kernel(
                     acc[u][i] = Ar{};
                 }
             }
+            // (chunks stay SMALL: the static grid-stride order interleaves
+            // the CTAs tile by tile, and so do small chunks; handing out the
+            // static share in chunks of 16-64 tiles instead -- every CTA alone
+            // in its own 0.25-1 MB -- cost fp32 / fp16 storage 5-40 %,
+            // profiles/r02_dot_pool_sweep.txt)
             const std::int64_t t0 = static_tiles + std::int64_t{c} * chunk_tiles;
             const std::int64_t t1 =
                 t0 + chunk_tiles < num_tiles ? t0 + chunk_tiles : num_tiles;

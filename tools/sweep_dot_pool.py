@@ -45,3 +45,4 @@ for st in (torch.float64, torch.float32, torch.float16):
     del x, y
 ab.tune("dot_pool_pct", 12)
 ab.tune("dot_chunk_tiles", 4)
+
