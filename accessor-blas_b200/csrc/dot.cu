@@ -210,9 +210,25 @@ __device__ __forceinline__ void finish_dot(Ar local, Ar* partials,
     // free, and the partials of the dynamic pool do not add fp32 rounding
     // steps to the result.
     __shared__ double wide_scratch[kWarp];
+    // (eight loads in flight per thread: one after the other, the ~16 L2 round
+    // trips of a 4000-entry fold were ~1 % of a 600 us call; the order of the
+    // additions is unchanged)
     double v = 0.0;
-    for (unsigned i = threadIdx.x; i < num_partials; i += BLOCK) {
-        v += static_cast<double>(__ldcg(partials + i));
+    constexpr unsigned kFoldLoads = 8;
+    for (unsigned base = threadIdx.x; base < num_partials;
+         base += BLOCK * kFoldLoads) {
+        Ar t[kFoldLoads];
+#pragma unroll
+        for (unsigned j = 0; j < kFoldLoads; ++j) {
+            const unsigned i = base + j * BLOCK;
+            t[j] = i < num_partials ? __ldcg(partials + i) : Ar{};
+        }
+#pragma unroll
+        for (unsigned j = 0; j < kFoldLoads; ++j) {
+            if (base + j * BLOCK < num_partials) {
+                v += static_cast<double>(t[j]);
+            }
+        }
     }
     Ar sum = static_cast<Ar>(block_sum(v, wide_scratch));
     if (px.world > 1) {
