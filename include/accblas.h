@@ -90,7 +90,11 @@ int accblas_gemv(accblas_handle_t handle, accblas_dtype ar, accblas_dtype st,
 
 /* *result = sum_i x[i*incx] * y[i*incy], accumulated in `ar` with a
  * deterministic two-pass tree (fixed for a given n, dtype pair and SM count),
- * written as `res` to the DEVICE pointer `result`. */
+ * written as `res` to the DEVICE pointer `result`.  Large contiguous operands:
+ * the last ~12 % of the data is handed to the SMs dynamically in small chunks
+ * (load balance), each chunk with its own partial sum folded in chunk order --
+ * the bits do not depend on which SM took which chunk.  The partials are
+ * folded in fp64 and rounded to `ar` once. */
 int accblas_dot(accblas_handle_t handle, accblas_dtype ar, accblas_dtype st,
                 accblas_dtype res, int64_t n, const void* x, int64_t incx,
                 const void* y, int64_t incy, void* result,
