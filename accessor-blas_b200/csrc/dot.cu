@@ -579,7 +579,11 @@ int launch_stream(Handle* h, std::int64_t n, const void* x, const void* y,
         // the chunk partials share the 64 KiB scratch with the CTA partials
         const std::int64_t room = max_grid - grid;
         const std::int64_t max_chunks = room < 4096 ? room : 4096;
+        // at least ~8 chunks per CTA, so that the pool still balances when
+        // it is small (n = 2^26: a 4-tile chunk is a tenth of a CTA's work)
         std::int64_t ct = tuning().dot_chunk_tiles;
+        const std::int64_t fine = pool / (8 * grid);
+        ct = ct < fine ? ct : (fine > 1 ? fine : 1);
         if (max_chunks > 0 && pool > 0) {
             const std::int64_t need = (pool + max_chunks - 1) / max_chunks;
             ct = ct > need ? ct : need;

@@ -26,6 +26,7 @@ for step in "$@"; do
     trsvab) timeout 600 python tools/trsv_ab.py > gpurun_out/${tag}_trsv_ab.log 2>&1; echo "trsvab rc=$?"; tail -30 gpurun_out/${tag}_trsv_ab.log ;;
     pytrsv) timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py -q -x -k trsv > gpurun_out/${tag}_pytrsv.log 2>&1; echo "pytrsv rc=$?"; tail -5 gpurun_out/${tag}_pytrsv.log ;;
     sweeppool) timeout 600 python tools/sweep_dot_pool.py > gpurun_out/${tag}_sweeppool.log 2>&1; echo "sweeppool rc=$?"; cat gpurun_out/${tag}_sweeppool.log ;;
+    sweeppool26) DOT_LOG2N=26 timeout 600 python tools/sweep_dot_pool.py > gpurun_out/${tag}_sweeppool26.log 2>&1; echo "sweeppool26 rc=$?"; cat gpurun_out/${tag}_sweeppool26.log ;;
     pydot) timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py -q -x -k "dot" > gpurun_out/${tag}_pydot.log 2>&1; echo "pydot rc=$?"; tail -5 gpurun_out/${tag}_pydot.log ;;
     sizes)  timeout 900 python tools/size_sweep.py > gpurun_out/${tag}_sizes.log 2>&1; echo "sizes rc=$?"; tail -3 gpurun_out/${tag}_sizes.log ;;
     bench)  timeout 900 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?" ;;

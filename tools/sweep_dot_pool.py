@@ -16,7 +16,8 @@ from oracle_binding import REF_LIB, RefKernels  # noqa: E402
 dev = torch.device("cuda:0")
 h = ab.Handle(0)
 refk = RefKernels() if REF_LIB.exists() else None
-nd = 2 ** 28
+import os
+nd = 2 ** int(os.environ.get("DOT_LOG2N", "28"))
 NAME = {torch.float64: "fp64", torch.float32: "fp32", torch.float16: "fp16"}
 src = torch.empty(2 * nd, dtype=torch.float64, device=dev)
 h.fill_uniform(1, 2 * nd, src, 2 * nd, 42, 0)
