@@ -735,7 +735,10 @@ def run_accblas_arm(args):
                          "frac": kernel_gbs / peak, "traffic": traffic,
                          "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                          "frac_of_nominal_8TBps": kernel_gbs / NOMINAL_HBM_GBS,
-                         "kernel": "accblas::gemv_stream_kernel<float,double,ROWS=4,UNROLL=2,RG=1,COLW=8>"},
+                         "kernel": "accblas::gemv_stream_kernel<float,double,ROWS=4,UNROLL=2,RG=1,COLW=8>",
+                         "timing": "launches BACK TO BACK on one stream between two CUDA events: consecutive "
+                                   "launches overlap their tail and ramp through programmatic dependent launch; "
+                                   "isolated calls (min of 10) are in `pairs`"},
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                     "api": "accblas_gemv_host (pinned host buffers)",
